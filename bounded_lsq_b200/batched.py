@@ -1,0 +1,224 @@
+"""Lock-step driver for B independent bounded problems (batched mode).
+
+One *round* = the user's residual/Jacobian callbacks on the current trial
+points, then two CUDA kernels through the C ABI (``include/blsq.h``):
+
+    blsq_linearise_batched   QR of [J | f] per problem      (HBM bound)
+    blsq_round_batched       ratio test + accept + next trial step (FP64)
+
+which together advance every running problem by exactly one trial evaluation
+of the reference's loops (trf.py:238-352 / dogbox.py:164-267).  The Jacobian is
+evaluated at every trial point (speculatively): an accepted step then needs no
+second pass, a rejected one reuses the factor kept in the state record.
+``nfev`` / ``njev`` are counted as the reference counts them (njev only on
+accepted steps).
+
+Finished problems are skipped inside the kernels; the host additionally
+compacts the active set (``idx``) so the callbacks only see running problems.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+
+EPS = 2.220446049250313e-16
+SQRT_EPS = EPS ** 0.5
+
+
+class PerProblem:
+    """Marks a callback argument as per-problem data with leading dimension B.
+
+    ``args=(PerProblem(y),)``: the callbacks receive ``y`` itself while every
+    problem is active and ``y[idx]`` once the active set has been compacted.
+    """
+
+    def __init__(self, tensor):
+        self.tensor = tensor
+
+
+def _gather_args(args, kwargs, idx):
+    def g(a):
+        if isinstance(a, PerProblem):
+            return a.tensor if idx is None else a.tensor.index_select(0, idx)
+        return a
+    return tuple(g(a) for a in args), {k: g(v) for k, v in kwargs.items()}
+
+
+class BatchedCallbacks:
+    """Adapts user callables ``fun(X, *args, **kwargs)`` to ``fun(X, idx)``."""
+
+    def __init__(self, fun, jac, args=(), kwargs=None, B=None):
+        self.fun, self.jac = fun, jac
+        self.args, self.kwargs = tuple(args), dict(kwargs or {})
+        self.B = B
+
+    def f(self, X, idx):
+        a, k = _gather_args(self.args, self.kwargs, idx)
+        return self.fun(X, *a, **k)
+
+    def j(self, X, idx):
+        a, k = _gather_args(self.args, self.kwargs, idx)
+        return self.jac(X, *a, **k)
+
+
+def _as_f64(t, like, what):
+    if not isinstance(t, torch.Tensor):
+        t = torch.as_tensor(t, dtype=torch.float64, device=like.device)
+    if t.dtype != torch.float64:
+        t = t.to(torch.float64)
+    if t.device != like.device:
+        t = t.to(like.device)
+    return t
+
+
+def solve_batched(lib, method, fun, jac, X0, lb, ub, ftol, xtol, gtol,
+                  max_nfev, scaling, diff_step=None, check_every=1,
+                  compact_below=0.75, trace=None):
+    """Run ``method`` ('trf' | 'dogbox') on B problems.
+
+    fun(X, idx) -> (A, m); jac is a callable jac(X, idx) -> (A, m, n) or the
+    string '2-point'.  X0 (B, n); lb/ub (n,) or (B, n); scaling (n,) tensor or
+    'jac'.  Returns a dict of device tensors (see least_squares_batched).
+    """
+    meth = {"trf": L.METHOD_TRF, "dogbox": L.METHOD_DOGBOX}[method]
+    dev = X0.device
+    f64 = torch.float64
+    B, n = X0.shape
+    if n > L.MAX_BATCHED_N:
+        raise ValueError(f"batched mode supports n <= {L.MAX_BATCHED_N}")
+    lib.check_tensor(X0, f64, "x0")
+    lib.check_tensor(lb, f64, "lb")
+    lib.check_tensor(ub, f64, "ub")
+    bstride = 0 if lb.dim() == 1 else n
+    lay = lib.state_layout(meth, n)
+    S = lay["size"]
+    LS = lib.lin_record_size(n)
+    if max_nfev is None:
+        max_nfev = 100 * n                           # trf.py:234-235
+    max_nfev = int(max_nfev)
+    jac_scaling = isinstance(scaling, str)
+    sc_ptr = None if jac_scaling else scaling.data_ptr()
+    if not jac_scaling:
+        lib.check_tensor(scaling, f64, "scaling")
+    fd = isinstance(jac, str)
+    rel = float("nan") if diff_step is None else float(diff_step)
+
+    state = torch.zeros((B, S), dtype=f64, device=dev)
+    istate = torch.zeros((B, L.ISTATE_SIZE), dtype=torch.int32, device=dev)
+    Xnew = torch.empty((B, n), dtype=f64, device=dev)
+    # dogbox evaluates J at the bound-snapped trial (dogbox.py:256-261)
+    Xjac = torch.empty((B, n), dtype=f64, device=dev) if method == "dogbox" \
+        else None
+    lin = torch.empty((B, LS), dtype=f64, device=dev)
+    count = torch.zeros(1, dtype=torch.int32, device=dev)
+    if fd:
+        Xp = torch.empty((n, B, n), dtype=f64, device=dev)
+        dx = torch.empty((B, n), dtype=f64, device=dev)
+    stream = lib.stream(X0)
+    lib.call("blsq_init_batched", meth, B, n, X0.data_ptr(), lb.data_ptr(),
+             ub.data_ptr(), bstride, state.data_ptr(), istate.data_ptr(),
+             Xnew.data_ptr(), stream)
+
+    idx = None          # int64 for torch gathers
+    idx32 = None        # int32 copy handed to the kernels
+    A = B
+    first = 1
+    m = None
+    rounds = 0
+    launches = 0
+    while A > 0:
+        Xa = Xnew[:A]
+        Xj = Xa if (Xjac is None or first) else Xjac[:A]
+        F = _as_f64(fun(Xa, idx), X0, "fun")
+        if F.dim() != 2 or F.shape[0] != A:
+            raise RuntimeError("batched `fun` must return an (A, m) tensor, "
+                               f"got {tuple(F.shape)} for A={A}")
+        F = F.contiguous()
+        if m is None:
+            m = F.shape[1]
+        elif F.shape[1] != m:
+            raise RuntimeError("`fun` changed its number of residuals")
+        ip = None if idx32 is None else idx32.data_ptr()
+        if not fd:
+            J = _as_f64(jac(Xj, idx), X0, "jac")
+            if J.dim() != 3 or J.shape[0] != A or J.shape[2] != n:
+                raise RuntimeError("batched `jac` must return an (A, m, n) "
+                                   f"tensor, got {tuple(J.shape)}")
+            if J.shape[1] != m:
+                raise RuntimeError(
+                    "Inconsistent dimensions between the returns of `fun` "
+                    "and `jac` on the first iteration.")
+            J = J.contiguous()
+            lib.call("blsq_linearise_batched", A, ip, m, n, F.data_ptr(),
+                     J.data_ptr(), None, None, 0, istate.data_ptr(),
+                     lin.data_ptr(), stream)
+        else:
+            Xpa = Xp.view(-1)[: n * A * n].view(n, A, n)
+            lib.call("blsq_fd2_points", A, ip, n, Xj.data_ptr(), lb.data_ptr(),
+                     ub.data_ptr(), bstride, rel, Xpa.data_ptr(),
+                     dx.data_ptr(), stream)
+            launches += 1
+            Fp = []
+            for i in range(n):
+                Fi = _as_f64(fun(Xpa[i], idx), X0, "fun").contiguous()
+                if Fi.shape != F.shape:
+                    raise RuntimeError("`fun` changed its output shape")
+                Fp.append(Fi)
+            plist = (C.c_void_p * n)(*[t.data_ptr() for t in Fp])
+            lib.call("blsq_linearise_batched", A, ip, m, n, F.data_ptr(), None,
+                     C.cast(plist, C.c_void_p), dx.data_ptr(), 1,
+                     istate.data_ptr(), lin.data_ptr(), stream)
+        lib.call("blsq_round_batched", meth, A, ip, m, n, lin.data_ptr(),
+                 X0.data_ptr(), lb.data_ptr(), ub.data_ptr(), bstride, sc_ptr,
+                 float(ftol), float(xtol), float(gtol), max_nfev, first,
+                 state.data_ptr(), istate.data_ptr(), Xnew.data_ptr(),
+                 None if Xjac is None else Xjac.data_ptr(), stream)
+        launches += 2
+        first = 0
+        rounds += 1
+        if trace is not None:
+            trace(rounds, idx, Xnew[:A], state, istate)
+        if rounds % check_every == 0 or rounds >= max_nfev:
+            st = istate[:, 0] if idx is None else istate[idx, 0]
+            running = st == L.STATUS_RUNNING
+            nrun = int(running.sum().item())          # the one host sync
+            if nrun == 0:
+                break
+            if nrun <= compact_below * A:
+                sel = running.nonzero(as_tuple=False).squeeze(1)
+                idx = sel if idx is None else idx.index_select(0, sel)
+                idx32 = idx.to(torch.int32)
+                Xnew[:nrun] = Xnew[:A].index_select(0, sel)
+                if Xjac is not None:
+                    Xjac[:nrun] = Xjac[:A].index_select(0, sel)
+                A = nrun
+        if rounds > max_nfev + 1:                     # cannot happen
+            raise RuntimeError("batched driver failed to terminate")
+
+    status = istate[:, 0].to(torch.int64)
+    bad = status < L.STATUS_RUNNING
+    if bool(bad.any().item()):
+        code = int(status[bad][0].item())
+        # trust_region.py:28-35 raises these from inside trf
+        if code == L.STATUS_ERR_TR_ZERO:
+            raise ValueError("`s` is zero.")
+        if code == L.STATUS_ERR_TR_OUTSIDE:
+            raise ValueError("`x` is not within the trust region.")
+        raise RuntimeError(f"internal status {code}")
+
+    x = state[:, lay["x"]:lay["x"] + n].contiguous()
+    if method == "trf":
+        # trf.py:257,354: find_active_constraints(x, lb, ub, rtol=xtol)
+        mask = lib.find_active_constraints(x, lb, ub, xtol)
+    else:
+        mask = torch.empty((B, n), dtype=torch.int64, device=dev)
+        lib.call("blsq_dogbox_on_bound", B, n, istate.data_ptr(),
+                 mask.data_ptr(), stream)
+    return dict(
+        x=x, obj_value=state[:, lay["obj"]].clone(),
+        optimality=state[:, lay["gnorm"]].clone(), active_mask=mask,
+        nfev=istate[:, 1].to(torch.int64), njev=istate[:, 2].to(torch.int64),
+        status=status, m=m, rounds=rounds, kernel_launches=launches)

@@ -1,0 +1,471 @@
+// Batched mode kernels + C ABI (include/blsq.h) for sm_100a.
+//
+// Two kernels per round of the lock-step solve:
+//
+//   lin_kernel    HBM-bound.  A group of 8/16/32 lanes owns one problem; the
+//                 lanes stream the rows of [J | f] with coalesced vector loads
+//                 straight into registers and run a modified Gram-Schmidt QR
+//                 with f as the last column, dot products reduced by warp
+//                 shuffles inside the group.  Output per problem: packed R,
+//                 Q^T f, g = J^T f, f.f  (a few hundred bytes).
+//   round_kernel  FP64-bound.  One thread owns one problem and runs the whole
+//                 n x n tail in registers (blsq_core.cuh): ratio test, accept,
+//                 Coleman-Li scaling, SVD, LM parameter, candidates, select.
+//
+// Reference lines each stage stands in for are cited in blsq_core.cuh and
+// include/blsq.h.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/blsq.h"
+#include "blsq_core.cuh"
+
+using namespace blsq;
+
+#define BLSQ_LAUNCH_CHECK()                                  \
+    do {                                                     \
+        cudaError_t e_ = cudaGetLastError();                 \
+        if (e_ != cudaSuccess) return (int)e_;               \
+    } while (0)
+
+namespace {
+
+// rows per lane held in registers by lin_kernel
+template <int N> struct LinCfg { static constexpr int RPL = (N <= 4) ? 8 : 4; };
+
+__device__ __forceinline__ double group_sum(double v, int G) {
+    for (int off = G >> 1; off > 0; off >>= 1)
+        v += __shfl_xor_sync(0xffffffffu, v, off, 32);
+    return v;
+}
+
+template <int N> struct PtrList { const double* p[N]; };
+
+// MODE 0: analytic J (A, m, n).  MODE 1: finite differences, Fpert.p[i] is
+// F at the i-th perturbed batch, (A, m); dx is (A, n).
+template <int N, int MODE>
+__global__ void __launch_bounds__(256)
+lin_kernel(int64_t A, const int32_t* __restrict__ idx, int m, int G,
+           const double* __restrict__ F, const double* __restrict__ J,
+           PtrList<N> Fpert, const double* __restrict__ dx,
+           const int32_t* __restrict__ istate, double* __restrict__ lin) {
+    constexpr int RPL = LinCfg<N>::RPL;
+    constexpr int C = N + 1;                      // columns of [J | f]
+    typedef LinRec<N> L;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t slot = tid / G;
+    const int lane = (int)(tid % G);
+    bool valid = slot < A;
+    if (valid) {
+        int64_t pid = idx ? idx[slot] : slot;
+        valid = istate[pid * IS_SIZE + IS_STATUS] == ST_RUNNING;
+    }
+    if (!__any_sync(0xffffffffu, valid)) return;
+
+    const double* Fp = F + slot * (int64_t)m;
+    const double* Jp = (MODE == 0) ? J + slot * (int64_t)m * N : nullptr;
+    double dxj[N];
+    if (MODE == 1) {
+#pragma unroll
+        for (int j = 0; j < N; j++)
+            dxj[j] = valid ? dx[slot * N + j] : 1.0;
+    }
+
+    double a[RPL + 1][C];
+    double r[N][C];
+    double gp[N], objp = 0.0;
+#pragma unroll
+    for (int j = 0; j < N; j++) gp[j] = 0.0;
+#pragma unroll
+    for (int k = 0; k < N; k++) {
+#pragma unroll
+        for (int j = 0; j < C; j++) r[k][j] = 0.0;
+    }
+
+    for (int base = 0; base < m; base += G * RPL) {
+        // ---- load this chunk: row (base + s*G + lane) -> a[s][*] ----
+#pragma unroll
+        for (int s = 0; s < RPL; s++) {
+            int row = base + s * G + lane;
+            bool ok = valid && row < m;
+            if (MODE == 0) {
+                if (ok) {
+                    const double* rp = Jp + (int64_t)row * N;
+                    if (N % 2 == 0) {
+#pragma unroll
+                        for (int j = 0; j < N; j += 2) {
+                            double2 t = __ldcs(reinterpret_cast<const double2*>(rp + j));
+                            a[s][j] = t.x;
+                            a[s][j + 1] = t.y;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < N; j++) a[s][j] = __ldcs(rp + j);
+                    }
+                    a[s][N] = __ldcs(Fp + row);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < C; j++) a[s][j] = 0.0;
+                }
+            } else {
+                if (ok) {
+                    double f0 = __ldcs(Fp + row);
+                    a[s][N] = f0;
+#pragma unroll
+                    for (int j = 0; j < N; j++)
+                        a[s][j] = __ldcs(Fpert.p[j] + slot * (int64_t)m + row);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < C; j++) a[s][j] = 0.0;
+                }
+            }
+        }
+        if (MODE == 1) {
+            // scipy _dense_difference: J[:, i] = (f(x + h_i e_i) - f0) / dx_i
+#pragma unroll
+            for (int s = 0; s < RPL; s++) {
+                int row = base + s * G + lane;
+                if (valid && row < m) {
+#pragma unroll
+                    for (int j = 0; j < N; j++)
+                        a[s][j] = (a[s][j] - a[s][N]) / dxj[j];
+                }
+            }
+        }
+        // ---- g = J^T f and f.f on the raw rows (trf.py:244, 229) ----
+#pragma unroll
+        for (int s = 0; s < RPL; s++) {
+#pragma unroll
+            for (int j = 0; j < N; j++) gp[j] = fma(a[s][j], a[s][N], gp[j]);
+            objp = fma(a[s][N], a[s][N], objp);
+        }
+        // ---- carry: row k of the running triangle lives on lane k ----
+#pragma unroll
+        for (int j = 0; j < C; j++) a[RPL][j] = 0.0;
+#pragma unroll
+        for (int k = 0; k < N; k++) {
+            if (lane == k) {
+#pragma unroll
+                for (int j = k; j < C; j++) a[RPL][j] = r[k][j];
+            }
+        }
+        // ---- modified Gram-Schmidt on the stacked (carry + chunk) rows ----
+#pragma unroll
+        for (int k = 0; k < N; k++) {
+            double dts[C];
+#pragma unroll
+            for (int j = k; j < C; j++) {
+                double acc = 0.0;
+#pragma unroll
+                for (int s = 0; s <= RPL; s++) acc = fma(a[s][k], a[s][j], acc);
+                dts[j] = group_sum(acc, G);
+            }
+            double dk = dts[k];
+            double rkk = sqrt(dk);
+            r[k][k] = rkk;
+#pragma unroll
+            for (int j = k + 1; j < C; j++) {
+                double coef = (dk > 0.0) ? dts[j] / dk : 0.0;
+                r[k][j] = (dk > 0.0) ? dts[j] / rkk : 0.0;
+#pragma unroll
+                for (int s = 0; s <= RPL; s++)
+                    a[s][j] = fma(-coef, a[s][k], a[s][j]);
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < N; j++) gp[j] = group_sum(gp[j], G);
+    objp = group_sum(objp, G);
+
+    if (valid) {
+        double* out = lin + slot * (int64_t)L::SIZE;
+        // lanes 0..N-1 write one row of the triangle each (+ their g, qtf)
+#pragma unroll
+        for (int k = 0; k < N; k++) {
+            if (lane == k) {
+#pragma unroll
+                for (int j = k; j < N; j++) out[L::R + tri_index<N>(k, j)] = r[k][j];
+                out[L::QTF + k] = r[k][N];
+                out[L::G + k] = gp[k];
+            }
+        }
+        if (lane == N % G) out[L::OBJ] = objp;
+    }
+}
+
+template <int N, int METHOD>
+__global__ void __launch_bounds__(128)
+round_kernel(int64_t A, const int32_t* __restrict__ idx,
+             const double* __restrict__ lin, const double* __restrict__ x0,
+             const double* __restrict__ lb, const double* __restrict__ ub,
+             int bstride, const double* __restrict__ scaling, SolveParams P,
+             int first, double* __restrict__ state,
+             int32_t* __restrict__ istate, double* __restrict__ Xnew,
+             double* __restrict__ Xjac) {
+    typedef LinRec<N> L;
+    constexpr int SS = (METHOD == BLSQ_METHOD_TRF) ? TrfState<N>::SIZE
+                                                   : DogState<N>::SIZE;
+    constexpr int XNEW = N;
+    const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= A) return;
+    const int64_t pid = idx ? idx[slot] : slot;
+    int ist[IS_SIZE];
+    int32_t* ip = istate + pid * IS_SIZE;
+    {
+        int4 t0 = *reinterpret_cast<const int4*>(ip);
+        int4 t1 = *reinterpret_cast<const int4*>(ip + 4);
+        ist[0] = t0.x; ist[1] = t0.y; ist[2] = t0.z; ist[3] = t0.w;
+        ist[4] = t1.x; ist[5] = t1.y; ist[6] = t1.z; ist[7] = t1.w;
+    }
+    if (ist[IS_STATUS] != ST_RUNNING) return;
+    double st[SS];
+    double* sp = state + pid * (int64_t)SS;
+#pragma unroll
+    for (int i = 0; i < SS; i++) st[i] = sp[i];
+    double ln[L::SIZE];
+    const double* lp = lin + slot * (int64_t)L::SIZE;
+#pragma unroll
+    for (int i = 0; i < L::SIZE; i += 2) {
+        double2 t = *reinterpret_cast<const double2*>(lp + i);
+        ln[i] = t.x;
+        ln[i + 1] = t.y;
+    }
+    double sc[N];
+#pragma unroll
+    for (int i = 0; i < N; i++) sc[i] = scaling ? scaling[i] : 1.0;
+    bool go;
+    if (METHOD == BLSQ_METHOD_TRF)
+        go = trf_round<N>(st, ist, ln, x0 + pid * N, lb + pid * bstride,
+                          ub + pid * bstride, sc, P, first);
+    else
+        go = dogbox_round<N>(st, ist, ln, x0 + pid * N, lb + pid * bstride,
+                             ub + pid * bstride, sc, P, first);
+#pragma unroll
+    for (int i = 0; i < SS; i++) sp[i] = st[i];
+    *reinterpret_cast<int4*>(ip) = make_int4(ist[0], ist[1], ist[2], ist[3]);
+    *reinterpret_cast<int4*>(ip + 4) = make_int4(ist[4], ist[5], ist[6], ist[7]);
+    if (go) {
+#pragma unroll
+        for (int i = 0; i < N; i++) Xnew[slot * N + i] = st[XNEW + i];
+        if (Xjac) {
+#pragma unroll
+            for (int i = 0; i < N; i++) {
+                double xj = st[XNEW + i];
+                if (METHOD == BLSQ_METHOD_DOGBOX) {
+                    // the point dogbox.py:256-261 would evaluate J at
+                    int ob = ((ist[IS_FREE] >> i) & 1) ? get2(ist[IS_MARKS], i)
+                                                       : get2(ist[IS_ONB], i);
+                    if (ob == -1) xj = lb[pid * bstride + i];
+                    if (ob == 1) xj = ub[pid * bstride + i];
+                }
+                Xjac[slot * N + i] = xj;
+            }
+        }
+    }
+}
+
+__global__ void init_kernel(int method, int64_t B, int n, int SS,
+                            const double* __restrict__ x0,
+                            const double* __restrict__ lb,
+                            const double* __restrict__ ub, int bstride,
+                            double* __restrict__ state,
+                            int32_t* __restrict__ istate,
+                            double* __restrict__ Xnew) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= B * n) return;
+    int64_t b = t / n;
+    int i = (int)(t % n);
+    double x = x0[t];
+    if (method == BLSQ_METHOD_TRF)
+        x = strictly_feasible(x, lb[b * bstride + i], ub[b * bstride + i], 1e-10);
+    state[b * SS + n + i] = x;          // XNEW
+    state[b * SS + i] = x;              // X
+    Xnew[t] = x;
+    if (i == 0) {
+        int32_t* ip = istate + b * IS_SIZE;
+        ip[IS_STATUS] = ST_RUNNING;
+#pragma unroll
+        for (int k = 1; k < IS_SIZE; k++) ip[k] = 0;
+    }
+}
+
+__global__ void on_bound_kernel(int64_t B, int n,
+                                const int32_t* __restrict__ istate,
+                                int64_t* __restrict__ mask) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= B * n) return;
+    int64_t b = t / n;
+    int i = (int)(t % n);
+    mask[t] = get2(istate[b * IS_SIZE + IS_ONB], i);
+}
+
+__global__ void count_running_kernel(int64_t B,
+                                     const int32_t* __restrict__ istate,
+                                     int32_t* __restrict__ count) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool run = t < B && istate[t * IS_SIZE + IS_STATUS] == ST_RUNNING;
+    unsigned bal = __ballot_sync(0xffffffffu, run);
+    if ((threadIdx.x & 31) == 0 && bal) atomicAdd(count, __popc(bal));
+}
+
+template <int N>
+int launch_lin(int64_t A, const int32_t* idx, int m, const double* F,
+               const double* J, const double* const* Fp_host, const double* dx,
+               int jac_mode, const int32_t* istate, double* lin,
+               cudaStream_t s) {
+    constexpr int RPL = LinCfg<N>::RPL;
+    int G = 8;
+    while (G < 32 && G * RPL < m) G <<= 1;
+    int64_t threads = A * G;
+    int64_t blocks = (threads + 255) / 256;
+    if (blocks > 0x7fffffff) return BLSQ_E_UNSUPPORTED;
+    PtrList<N> pl;
+    for (int j = 0; j < N; j++) pl.p[j] = (jac_mode == 1) ? Fp_host[j] : nullptr;
+    if (jac_mode == 0)
+        lin_kernel<N, 0><<<(unsigned)blocks, 256, 0, s>>>(A, idx, m, G, F, J, pl, dx, istate, lin);
+    else
+        lin_kernel<N, 1><<<(unsigned)blocks, 256, 0, s>>>(A, idx, m, G, F, J, pl, dx, istate, lin);
+    BLSQ_LAUNCH_CHECK();
+    return 0;
+}
+
+template <int N>
+int launch_round(int method, int64_t A, const int32_t* idx, const double* lin,
+                 const double* x0, const double* lb, const double* ub,
+                 int bstride, const double* scaling, SolveParams P, int first,
+                 double* state, int32_t* istate, double* Xnew, double* Xjac,
+                 cudaStream_t s) {
+    int64_t blocks = (A + 127) / 128;
+    if (blocks > 0x7fffffff) return BLSQ_E_UNSUPPORTED;
+    if (method == BLSQ_METHOD_TRF)
+        round_kernel<N, BLSQ_METHOD_TRF><<<(unsigned)blocks, 128, 0, s>>>(
+            A, idx, lin, x0, lb, ub, bstride, scaling, P, first, state, istate, Xnew, Xjac);
+    else
+        round_kernel<N, BLSQ_METHOD_DOGBOX><<<(unsigned)blocks, 128, 0, s>>>(
+            A, idx, lin, x0, lb, ub, bstride, scaling, P, first, state, istate, Xnew, Xjac);
+    BLSQ_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace
+
+#define BLSQ_DISPATCH_N(n, CALL)          \
+    switch (n) {                          \
+        case 1: { constexpr int N_ = 1; CALL; } break; \
+        case 2: { constexpr int N_ = 2; CALL; } break; \
+        case 3: { constexpr int N_ = 3; CALL; } break; \
+        case 4: { constexpr int N_ = 4; CALL; } break; \
+        case 5: { constexpr int N_ = 5; CALL; } break; \
+        case 6: { constexpr int N_ = 6; CALL; } break; \
+        case 7: { constexpr int N_ = 7; CALL; } break; \
+        case 8: { constexpr int N_ = 8; CALL; } break; \
+        default: return BLSQ_E_UNSUPPORTED; \
+    }
+
+extern "C" {
+
+int blsq_state_layout(int method, int n, int* out) {
+    if (!out) return BLSQ_E_BADARG;
+    if (method != BLSQ_METHOD_TRF && method != BLSQ_METHOD_DOGBOX) return BLSQ_E_BADARG;
+    BLSQ_DISPATCH_N(n, {
+        if (method == BLSQ_METHOD_TRF) {
+            typedef TrfState<N_> S;
+            out[0] = S::SIZE; out[1] = S::X; out[2] = S::XNEW; out[3] = S::SCALE;
+            out[4] = S::OBJ; out[5] = S::DELTA; out[6] = S::GNORM; out[7] = S::G;
+            out[8] = S::ALPHA;
+        } else {
+            typedef DogState<N_> S;
+            out[0] = S::SIZE; out[1] = S::X; out[2] = S::XNEW; out[3] = S::SCALE;
+            out[4] = S::OBJ; out[5] = S::DELTA; out[6] = S::GNORM; out[7] = S::G;
+            out[8] = -1;
+        }
+    });
+    return 0;
+}
+
+int blsq_lin_record_size(int n) {
+    BLSQ_DISPATCH_N(n, { return LinRec<N_>::SIZE; });
+    return BLSQ_E_UNSUPPORTED;
+}
+
+int blsq_init_batched(int method, int64_t B, int n, const double* x0,
+                      const double* lb, const double* ub, int bstride,
+                      double* state, int32_t* istate, double* Xnew,
+                      void* stream) {
+    if (B < 0 || !x0 || !lb || !ub || !state || !istate || !Xnew) return BLSQ_E_BADARG;
+    if (bstride != 0 && bstride != n) return BLSQ_E_BADARG;
+    int lay[9];
+    int rc = blsq_state_layout(method, n, lay);
+    if (rc) return rc;
+    if (B == 0) return 0;
+    int64_t blocks = (B * n + 255) / 256;
+    init_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        method, B, n, lay[0], x0, lb, ub, bstride, state, istate, Xnew);
+    BLSQ_LAUNCH_CHECK();
+    return 0;
+}
+
+int blsq_linearise_batched(int64_t A, const int32_t* idx, int m, int n,
+                           const double* F, const double* J,
+                           const double* const* Fp_host, const double* dx,
+                           int jac_mode, const int32_t* istate, double* lin,
+                           void* stream) {
+    if (A < 0 || m < 1 || !F || !istate || !lin) return BLSQ_E_BADARG;
+    if (jac_mode != 0 && jac_mode != 1) return BLSQ_E_BADARG;
+    if (jac_mode == 0 && !J) return BLSQ_E_BADARG;
+    if (jac_mode == 1 && (!dx || !Fp_host)) return BLSQ_E_BADARG;
+    if (jac_mode == 1)
+        for (int j = 0; j < n && j < BLSQ_MAX_BATCHED_N; j++)
+            if (!Fp_host[j]) return BLSQ_E_BADARG;
+    if (A == 0) return 0;
+    BLSQ_DISPATCH_N(n, {
+        return launch_lin<N_>(A, idx, m, F, J, Fp_host, dx, jac_mode, istate,
+                              lin, (cudaStream_t)stream);
+    });
+    return 0;
+}
+
+int blsq_round_batched(int method, int64_t A, const int32_t* idx, int m, int n,
+                       const double* lin, const double* x0, const double* lb,
+                       const double* ub, int bstride, const double* scaling,
+                       double ftol, double xtol, double gtol, int max_nfev,
+                       int first, double* state, int32_t* istate, double* Xnew,
+                       double* Xjac, void* stream) {
+    if (A < 0 || !lin || !x0 || !lb || !ub || !state || !istate || !Xnew) return BLSQ_E_BADARG;
+    if (method != BLSQ_METHOD_TRF && method != BLSQ_METHOD_DOGBOX) return BLSQ_E_BADARG;
+    if (bstride != 0 && bstride != n) return BLSQ_E_BADARG;
+    if (A == 0) return 0;
+    SolveParams P;
+    P.ftol = ftol; P.xtol = xtol; P.gtol = gtol;
+    P.max_nfev = max_nfev; P.m = m; P.jac_scaling = scaling ? 0 : 1;
+    BLSQ_DISPATCH_N(n, {
+        return launch_round<N_>(method, A, idx, lin, x0, lb, ub, bstride,
+                                scaling, P, first, state, istate, Xnew, Xjac,
+                                (cudaStream_t)stream);
+    });
+    return 0;
+}
+
+int blsq_dogbox_on_bound(int64_t B, int n, const int32_t* istate,
+                         int64_t* mask, void* stream) {
+    if (B < 0 || n < 1 || n > BLSQ_MAX_BATCHED_N || !istate || !mask) return BLSQ_E_BADARG;
+    if (B == 0) return 0;
+    int64_t blocks = (B * n + 255) / 256;
+    on_bound_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(B, n, istate, mask);
+    BLSQ_LAUNCH_CHECK();
+    return 0;
+}
+
+int blsq_count_running(int64_t B, const int32_t* istate, int32_t* count,
+                       void* stream) {
+    if (B < 0 || !istate || !count) return BLSQ_E_BADARG;
+    cudaError_t e = cudaMemsetAsync(count, 0, sizeof(int32_t), (cudaStream_t)stream);
+    if (e != cudaSuccess) return (int)e;
+    if (B == 0) return 0;
+    int64_t blocks = (B + 255) / 256;
+    count_running_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(B, istate, count);
+    BLSQ_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,292 @@
+// Elementwise bound-geometry passes and finite-difference points: pure
+// HBM-bandwidth kernels, bit-exact with bounds.py / dogbox.py:9-35 / scipy
+// _numdiff (see blsq_core.cuh for the arithmetic, include/blsq.h for the ABI).
+//
+// Layout: x is (B, n) row-major; one thread per element so a warp touches 32
+// consecutive doubles.  The two row reductions (step_size_to_bound's min and
+// in_bounds' all) give each row to a power-of-two group of lanes and reduce
+// with shuffles.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/blsq.h"
+#include "blsq_core.cuh"
+
+using namespace blsq;
+
+#define BLSQ_LAUNCH_CHECK()                                  \
+    do {                                                     \
+        cudaError_t e_ = cudaGetLastError();                 \
+        if (e_ != cudaSuccess) return (int)e_;               \
+    } while (0)
+
+namespace {
+
+__device__ __forceinline__ int64_t gtid() {
+    return (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+}
+
+int group_for(int n) {
+    int G = 1;
+    while (G < 32 && G < n) G <<= 1;
+    return G;
+}
+
+__global__ void step_size_kernel(int64_t B, int n, int G,
+                                 const double* __restrict__ x,
+                                 const double* __restrict__ d,
+                                 const double* __restrict__ lb,
+                                 const double* __restrict__ ub, int bstride,
+                                 double* __restrict__ step,
+                                 int64_t* __restrict__ hits) {
+    int64_t t = gtid();
+    int64_t b = t / G;
+    int lane = (int)(t % G);
+    bool valid = b < B;
+    // pass 1: row minimum (NaN-propagating like np.min)
+    double tmin = dinf();
+    bool has_nan = false;
+    if (valid) {
+        for (int i = lane; i < n; i += G) {
+            double di = d[b * n + i];
+            double ti = dinf();
+            if (di != 0) {
+                double xi = x[b * n + i];
+                ti = np_max((lb[b * bstride + i] - xi) / di,
+                            (ub[b * bstride + i] - xi) / di);
+            }
+            if (ti != ti) has_nan = true;
+            if (ti < tmin) tmin = ti;
+        }
+    }
+    for (int off = G >> 1; off > 0; off >>= 1) {
+        double o = __shfl_xor_sync(0xffffffffu, tmin, off, 32);
+        bool on = __shfl_xor_sync(0xffffffffu, (int)has_nan, off, 32);
+        if (o < tmin) tmin = o;
+        has_nan = has_nan || on;
+    }
+    if (has_nan) tmin = dnan();
+    if (!valid) return;
+    if (lane == 0) step[b] = tmin;
+    if (hits) {
+        for (int i = lane; i < n; i += G) {
+            double di = d[b * n + i];
+            double ti = dinf();
+            if (di != 0) {
+                double xi = x[b * n + i];
+                ti = np_max((lb[b * bstride + i] - xi) / di,
+                            (ub[b * bstride + i] - xi) / di);
+            }
+            hits[b * n + i] = (ti == tmin) ? isign(di) : 0;
+        }
+    }
+}
+
+__global__ void in_bounds_kernel(int64_t B, int n, int G,
+                                 const double* __restrict__ x,
+                                 const double* __restrict__ lb,
+                                 const double* __restrict__ ub, int bstride,
+                                 uint8_t* __restrict__ ok) {
+    int64_t t = gtid();
+    int64_t b = t / G;
+    int lane = (int)(t % G);
+    bool valid = b < B;
+    int good = 1;
+    if (valid) {
+        for (int i = lane; i < n; i += G) {
+            double xi = x[b * n + i];
+            good &= (int)((xi >= lb[b * bstride + i]) & (xi <= ub[b * bstride + i]));
+        }
+    }
+    for (int off = G >> 1; off > 0; off >>= 1)
+        good &= __shfl_xor_sync(0xffffffffu, good, off, 32);
+    if (valid && lane == 0) ok[b] = (uint8_t)good;
+}
+
+__global__ void active_kernel(int64_t total, int n, const double* __restrict__ x,
+                              const double* __restrict__ lb,
+                              const double* __restrict__ ub, int bstride,
+                              double rtol, int64_t* __restrict__ mask) {
+    int64_t t = gtid();
+    if (t >= total) return;
+    int64_t b = t / n;
+    int i = (int)(t % n);
+    mask[t] = active_constraint(x[t], lb[b * bstride + i], ub[b * bstride + i], rtol);
+}
+
+__global__ void feasible_kernel(int64_t total, int n, const double* __restrict__ x,
+                                const double* __restrict__ lb,
+                                const double* __restrict__ ub, int bstride,
+                                double rstep, double* __restrict__ out) {
+    int64_t t = gtid();
+    if (t >= total) return;
+    int64_t b = t / n;
+    int i = (int)(t % n);
+    out[t] = strictly_feasible(x[t], lb[b * bstride + i], ub[b * bstride + i], rstep);
+}
+
+__global__ void cl_kernel(int64_t total, int n, const double* __restrict__ x,
+                          const double* __restrict__ g,
+                          const double* __restrict__ lb,
+                          const double* __restrict__ ub, int bstride,
+                          double* __restrict__ v, double* __restrict__ jv) {
+    int64_t t = gtid();
+    if (t >= total) return;
+    int64_t b = t / n;
+    int i = (int)(t % n);
+    double vv, jj;
+    cl_scaling(x[t], g[t], lb[b * bstride + i], ub[b * bstride + i], vv, jj);
+    v[t] = vv;
+    jv[t] = jj;
+}
+
+__global__ void intersection_kernel(int64_t total, int n,
+                                    const double* __restrict__ x,
+                                    const double* __restrict__ tr,
+                                    const double* __restrict__ lb,
+                                    const double* __restrict__ ub, int bstride,
+                                    double* __restrict__ lo,
+                                    double* __restrict__ hi,
+                                    uint8_t* __restrict__ flags) {
+    int64_t t = gtid();
+    if (t >= total) return;
+    int64_t b = t / n;
+    int i = (int)(t % n);
+    double l, h;
+    int f = find_intersection(x[t], tr[t], lb[b * bstride + i], ub[b * bstride + i], l, h);
+    lo[t] = l;
+    hi[t] = h;
+    flags[t] = (uint8_t)f;
+}
+
+// one thread per (i, slot, k): Xp[i, slot, k] = x_k (+ h_i when k == i)
+__global__ void fd2_points_kernel(int64_t A, const int32_t* __restrict__ idx,
+                                  int n, const double* __restrict__ x,
+                                  const double* __restrict__ lb,
+                                  const double* __restrict__ ub, int bstride,
+                                  double rel_step, double* __restrict__ Xp,
+                                  double* __restrict__ dx) {
+    int64_t t = gtid();
+    int64_t total = A * n * n;
+    if (t >= total) return;
+    int k = (int)(t % n);
+    int64_t slot = (t / n) % A;
+    int i = (int)(t / ((int64_t)n * A));
+    double xk = x[slot * n + k];
+    if (k == i) {
+        int64_t pid = idx ? idx[slot] : slot;
+        double h = fd2_step(xk, lb[pid * bstride + k], ub[pid * bstride + k], rel_step);
+        double xp = xk + h;
+        dx[slot * n + i] = xp - xk;
+        xk = xp;
+    }
+    Xp[t] = xk;
+}
+
+}  // namespace
+
+extern "C" {
+
+int blsq_version(void) { return BLSQ_VERSION; }
+
+const char* blsq_error_string(int code) {
+    if (code == 0) return "ok";
+    if (code == BLSQ_E_BADARG) return "invalid argument";
+    if (code == BLSQ_E_UNSUPPORTED) return "unsupported size";
+    if (code > 0) return cudaGetErrorString((cudaError_t)code);
+    return "unknown error";
+}
+
+#define BLSQ_CHECK_COMMON(B, n, bstride)                        \
+    if ((B) < 0 || (n) < 1) return BLSQ_E_BADARG;               \
+    if ((bstride) != 0 && (bstride) != (n)) return BLSQ_E_BADARG; \
+    if ((B) == 0) return 0;
+
+int blsq_step_size_to_bound(int64_t B, int n, const double* x, const double* d,
+                            const double* lb, const double* ub, int bstride,
+                            double* step, int64_t* hits, void* stream) {
+    if (!x || !d || !lb || !ub || !step) return BLSQ_E_BADARG;
+    BLSQ_CHECK_COMMON(B, n, bstride)
+    int G = group_for(n);
+    int64_t blocks = (B * G + 255) / 256;
+    step_size_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        B, n, G, x, d, lb, ub, bstride, step, hits);
+    BLSQ_LAUNCH_CHECK();
+    return 0;
+}
+
+int blsq_in_bounds(int64_t B, int n, const double* x, const double* lb,
+                   const double* ub, int bstride, uint8_t* ok, void* stream) {
+    if (!x || !lb || !ub || !ok) return BLSQ_E_BADARG;
+    BLSQ_CHECK_COMMON(B, n, bstride)
+    int G = group_for(n);
+    int64_t blocks = (B * G + 255) / 256;
+    in_bounds_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        B, n, G, x, lb, ub, bstride, ok);
+    BLSQ_LAUNCH_CHECK();
+    return 0;
+}
+
+int blsq_find_active_constraints(int64_t B, int n, const double* x,
+                                 const double* lb, const double* ub,
+                                 int bstride, double rtol, int64_t* mask,
+                                 void* stream) {
+    if (!x || !lb || !ub || !mask) return BLSQ_E_BADARG;
+    BLSQ_CHECK_COMMON(B, n, bstride)
+    int64_t total = B * n;
+    active_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        total, n, x, lb, ub, bstride, rtol, mask);
+    BLSQ_LAUNCH_CHECK();
+    return 0;
+}
+
+int blsq_make_strictly_feasible(int64_t B, int n, const double* x,
+                                const double* lb, const double* ub, int bstride,
+                                double rstep, double* out, void* stream) {
+    if (!x || !lb || !ub || !out) return BLSQ_E_BADARG;
+    BLSQ_CHECK_COMMON(B, n, bstride)
+    int64_t total = B * n;
+    feasible_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        total, n, x, lb, ub, bstride, rstep, out);
+    BLSQ_LAUNCH_CHECK();
+    return 0;
+}
+
+int blsq_scaling_vector(int64_t B, int n, const double* x, const double* g,
+                        const double* lb, const double* ub, int bstride,
+                        double* v, double* jv, void* stream) {
+    if (!x || !g || !lb || !ub || !v || !jv) return BLSQ_E_BADARG;
+    BLSQ_CHECK_COMMON(B, n, bstride)
+    int64_t total = B * n;
+    cl_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        total, n, x, g, lb, ub, bstride, v, jv);
+    BLSQ_LAUNCH_CHECK();
+    return 0;
+}
+
+int blsq_find_intersection(int64_t B, int n, const double* x, const double* tr,
+                           const double* lb, const double* ub, int bstride,
+                           double* lo, double* hi, uint8_t* flags,
+                           void* stream) {
+    if (!x || !tr || !lb || !ub || !lo || !hi || !flags) return BLSQ_E_BADARG;
+    BLSQ_CHECK_COMMON(B, n, bstride)
+    int64_t total = B * n;
+    intersection_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        total, n, x, tr, lb, ub, bstride, lo, hi, flags);
+    BLSQ_LAUNCH_CHECK();
+    return 0;
+}
+
+int blsq_fd2_points(int64_t A, const int32_t* idx, int n, const double* x,
+                    const double* lb, const double* ub, int bstride,
+                    double rel_step, double* Xp, double* dx, void* stream) {
+    if (!x || !lb || !ub || !Xp || !dx) return BLSQ_E_BADARG;
+    BLSQ_CHECK_COMMON(A, n, bstride)
+    int64_t total = A * n * n;
+    fd2_points_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        A, idx, n, x, lb, ub, bstride, rel_step, Xp, dx);
+    BLSQ_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // extern "C"

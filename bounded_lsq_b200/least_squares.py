@@ -1,0 +1,311 @@
+"""``least_squares`` front end with the reference's surface.
+
+Mirrors ``bounded_lsq/least_squares.py:120-383`` (argument validation,
+callback wrapping, method dispatch, messages) for ``method='trf'|'dogbox'``;
+the iterations run in the sm_100a kernels behind ``include/blsq.h``.
+
+Two entry points:
+
+``least_squares``          one problem, exactly the reference's semantics
+                           (``x0`` at most 1-D).  Callbacks receive / return
+                           torch CUDA float64 tensors.
+``least_squares_batched``  B independent problems in lock step: ``x0`` is
+                           (B, n), ``fun(X, ...) -> (A, m)``,
+                           ``jac(X, ...) -> (A, m, n)``; per-problem callback
+                           data is passed as ``PerProblem(tensor)`` in ``args``.
+
+No CPU path: tensors must be CUDA tensors and the CUDA library must be built.
+"""
+from __future__ import annotations
+
+from warnings import warn
+
+import torch
+
+from . import _lib as L
+from .batched import PerProblem, BatchedCallbacks, solve_batched
+
+EPS = 2.220446049250313e-16
+SQRT_EPS = EPS ** 0.5
+
+# least_squares.py:30-37
+TERMINATION_MESSAGES = {
+    0: "The maximum number of function evaluations is exceeded.",
+    1: "`gtol` termination condition is satisfied.",
+    2: "`ftol` termination condition is satisfied.",
+    3: "`xtol` termination condition is satisfied.",
+    4: "Both `ftol` and `xtol` termination conditions are satisfied.",
+}
+
+
+class OptimizeResult(dict):
+    """Attribute-access dict with the fields of scipy's OptimizeResult
+    (least_squares.py:206-252)."""
+
+    def __getattr__(self, name):
+        try:
+            return self[name]
+        except KeyError as e:
+            raise AttributeError(name) from e
+
+    __setattr__ = dict.__setitem__
+    __delattr__ = dict.__delitem__
+
+    def __dir__(self):
+        return list(self.keys())
+
+
+def check_tolerance(ftol, xtol, gtol):
+    """least_squares.py:15-27."""
+    message = "{} is too low, setting to machine epsilon {}."
+    if ftol < EPS:
+        warn(message.format("`ftol`", EPS))
+        ftol = EPS
+    if xtol < EPS:
+        warn(message.format("`xtol`", EPS))
+        xtol = EPS
+    if gtol < EPS:
+        warn(message.format("`gtol`", EPS))
+        gtol = EPS
+    return ftol, xtol, gtol
+
+
+def _default_device():
+    if not torch.cuda.is_available():
+        raise L.BlsqError("bounded_lsq_b200 needs a CUDA device (sm_100a); "
+                          "there is no CPU path")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _to_f64(a, device):
+    if isinstance(a, torch.Tensor):
+        return a.to(device=device, dtype=torch.float64)
+    return torch.as_tensor(a, dtype=torch.float64, device=device)
+
+
+def prepare_bounds(bounds, x0):
+    """bounds.py:7-16 -- scalar bounds are expanded to x0's last dimension."""
+    lb, ub = (_to_f64(b, x0.device) for b in bounds)
+    n = x0.shape[-1]
+    if lb.dim() == 0:
+        lb = lb.expand(n).contiguous()
+    if ub.dim() == 0:
+        ub = ub.expand(n).contiguous()
+    return lb.contiguous(), ub.contiguous()
+
+
+def check_scaling(scaling, x0):
+    """least_squares.py:100-117 (shared across the batch: shape (n,))."""
+    if isinstance(scaling, str) and scaling == 'jac':
+        return scaling
+    try:
+        scaling = _to_f64(scaling, x0.device)
+    except (ValueError, TypeError, RuntimeError):
+        raise ValueError("`scaling` must be 'jac' or array-like with numbers.")
+    if bool(torch.any(scaling <= 0).item()):
+        raise ValueError("`scaling` must contain only positive values.")
+    n = x0.shape[-1]
+    if scaling.dim() == 0:
+        scaling = scaling.expand(n)
+    if scaling.shape != (n,):
+        raise ValueError("Inconsistent shapes between `scaling` and `x0`.")
+    return scaling.contiguous()
+
+
+def _validate_common(method, bounds, jac):
+    if method == 'lm':
+        raise ValueError("`method='lm'` (MINPACK wrapper, least_squares.py:"
+                         "52-97) is outside the B200 hot path; use 'trf' or "
+                         "'dogbox'.")
+    if method not in ('trf', 'dogbox'):
+        raise ValueError("`method` must be 'dogbox', 'trf' or 'lm'.")
+    if len(bounds) != 2:
+        raise ValueError("`bounds` must contain 2 elements.")
+    if jac not in ('2-point', '3-point') and not callable(jac):
+        raise ValueError("`jac` must be '2-point', '3-point' or callable.")
+    if jac == '3-point':
+        raise NotImplementedError(
+            "jac='3-point' is not built yet (SURVEY 8f rank 1); use "
+            "'2-point' or a callable")
+
+
+def least_squares_batched(fun, x0, jac='2-point', bounds=(-float('inf'), float('inf')),
+                          method='trf', ftol=SQRT_EPS, xtol=SQRT_EPS,
+                          gtol=SQRT_EPS, max_nfev=None, scaling=1.0,
+                          diff_step=None, args=(), kwargs={}, options={},
+                          _lib=None):
+    """Solve B independent bounded problems (same n, m, method, tolerances).
+
+    x0 : (B, n).  bounds : scalars, (n,) or (B, n) tensors.
+    fun(X, *args, **kwargs) -> (A, m) and jac(X, *args, **kwargs) -> (A, m, n)
+    are called on the A <= B problems still running (rows in problem order);
+    wrap per-problem tensors in ``PerProblem`` so they are gathered alike.
+    Every field of the result has a leading B dimension.
+    """
+    lib = _lib if _lib is not None else L.get_lib()
+    _validate_common(method, bounds, jac)
+    if not isinstance(x0, torch.Tensor):
+        dev = _default_device() if lib.requires_cuda else torch.device("cpu")
+        x0 = torch.as_tensor(x0, dtype=torch.float64, device=dev)
+    x0 = x0.to(torch.float64).contiguous()
+    if x0.dim() != 2:
+        raise ValueError("batched `x0` must be (B, n).")
+    B, n = x0.shape
+    lb, ub = prepare_bounds(bounds, x0)
+    for b in (lb, ub):
+        if b.shape != (n,) and b.shape != (B, n):
+            raise ValueError("Inconsistent shapes between bounds and `x0`.")
+    if lb.shape != ub.shape:
+        lb = lb.expand(B, n).contiguous()
+        ub = ub.expand(B, n).contiguous()
+    if bool(torch.any(lb >= ub).item()):
+        raise ValueError("Each lower bound mush be strictly less than each "
+                         "upper bound.")
+    scaling = check_scaling(scaling, x0)
+    ftol, xtol, gtol = check_tolerance(ftol, xtol, gtol)
+    if not bool(lib.in_bounds(x0, lb, ub).all().item()):
+        raise ValueError("`x0` is infeasible.")
+
+    cb = BatchedCallbacks(fun, jac, args, kwargs, B)
+    jarg = jac if isinstance(jac, str) else cb.j
+    out = solve_batched(lib, method, cb.f, jarg, x0, lb, ub, ftol, xtol, gtol,
+                        max_nfev, scaling, diff_step=diff_step, **options)
+    res = OptimizeResult(out)
+    res.fun = cb.f(res.x, None)
+    res.x_covariance = None
+    res.message = TERMINATION_MESSAGES
+    res.success = res.status > 0
+    return res
+
+
+def _single_callbacks(fun, jac, args, kwargs, dev):
+    """least_squares.py:351-371 on top of the (A=1, ...) batched protocol."""
+
+    def fun_b(X, idx=None):
+        f = fun(X[0], *args, **kwargs)
+        f = _to_f64(f, dev)
+        if f.dim() == 0:
+            f = f.reshape(1)
+        if f.dim() > 1:
+            raise RuntimeError("`fun` must return at most 1-d array_like.")
+        return f.reshape(1, -1)
+
+    if not callable(jac):
+        return fun_b, jac
+
+    def jac_b(X, idx=None):
+        J = jac(X[0], *args, **kwargs)
+        J = _to_f64(J, dev)
+        if J.dim() > 2:
+            raise RuntimeError("`jac` must return at most 2-d array_like.")
+        while J.dim() < 2:
+            J = J.unsqueeze(0)
+        return J.unsqueeze(0)
+
+    return fun_b, jac_b
+
+
+def least_squares(fun, x0, jac='2-point', bounds=(-float('inf'), float('inf')),
+                  method='trf', ftol=SQRT_EPS, xtol=SQRT_EPS, gtol=SQRT_EPS,
+                  max_nfev=None, scaling=1.0, diff_step=None, args=(),
+                  kwargs={}, options={}, _lib=None):
+    """Drop-in for ``bounded_lsq.least_squares`` (least_squares.py:120-383),
+    methods 'trf' and 'dogbox'.
+
+    ``fun(x, *args, **kwargs)`` receives a 1-D float64 CUDA tensor and returns
+    the residuals as a tensor (or scalar); ``jac`` likewise returns (m, n).
+    Result fields that are arrays in the reference are CUDA tensors here.
+    """
+    lib = _lib if _lib is not None else L.get_lib()
+    _validate_common(method, bounds, jac)
+    if isinstance(x0, torch.Tensor):
+        dev = x0.device
+    else:
+        dev = _default_device() if lib.requires_cuda else torch.device("cpu")
+    x0 = _to_f64(x0, dev)
+    if x0.dim() == 0:
+        x0 = x0.reshape(1)
+    if x0.dim() > 1:
+        raise ValueError("`x0` must have at most 1 dimension.")
+    n = x0.shape[0]
+    lb, ub = prepare_bounds(bounds, x0)
+    if lb.shape != x0.shape or ub.shape != x0.shape:
+        raise ValueError("Inconsistent shapes between bounds and `x0`.")
+    if bool(torch.any(lb >= ub).item()):
+        raise ValueError("Each lower bound mush be strictly less than each "
+                         "upper bound.")
+    scaling = check_scaling(scaling, x0)
+    ftol, xtol, gtol = check_tolerance(ftol, xtol, gtol)
+    X0 = x0.reshape(1, n).contiguous()
+    if not bool(lib.in_bounds(X0, lb, ub).all().item()):
+        raise ValueError("`x0` is infeasible.")
+
+    if n > L.MAX_BATCHED_N:
+        from .tall import solve_tall
+        return solve_tall(lib, method, fun, jac, x0, lb, ub, ftol, xtol, gtol,
+                          max_nfev, scaling, diff_step, args, kwargs, options)
+
+    fun_b, jac_b = _single_callbacks(fun, jac, tuple(args), dict(kwargs), dev)
+    out = solve_batched(lib, method, fun_b, jac_b, X0, lb, ub, ftol, xtol,
+                        gtol, max_nfev, scaling, diff_step=diff_step,
+                        **options)
+    x = out["x"][0]
+    res = OptimizeResult(
+        x=x, fun=fun_b(x.reshape(1, n))[0], obj_value=float(out["obj_value"][0]),
+        optimality=float(out["optimality"][0]),
+        active_mask=out["active_mask"][0], nfev=int(out["nfev"][0]),
+        njev=int(out["njev"][0]), status=int(out["status"][0]),
+        x_covariance=None)
+    if callable(jac):
+        res.jac = jac_b(x.reshape(1, n))[0]
+    else:
+        res.jac = fd_jacobian(lib, fun_b, x, res.fun, lb, ub, diff_step)
+    res.message = TERMINATION_MESSAGES[res.status]
+    res.success = res.status > 0
+    return res
+
+
+def fd_jacobian(lib, fun_b, x, f0, lb, ub, diff_step=None):
+    """Dense 2-point Jacobian (m, n) at one point, through blsq_fd2_points."""
+    n = x.shape[0]
+    Xp = torch.empty((n, 1, n), dtype=torch.float64, device=x.device)
+    dx = torch.empty((1, n), dtype=torch.float64, device=x.device)
+    rel = float("nan") if diff_step is None else float(diff_step)
+    lib.call("blsq_fd2_points", 1, None, n, x.contiguous().data_ptr(),
+             lb.data_ptr(), ub.data_ptr(), 0, rel, Xp.data_ptr(),
+             dx.data_ptr(), lib.stream(x))
+    cols = [(fun_b(Xp[i])[0] - f0) / dx[0, i] for i in range(n)]
+    return torch.stack(cols, dim=1)
+
+
+def trf(fun, jac, x0, lb, ub, ftol, xtol, gtol, max_nfev, scaling, **options):
+    """Positional signature of ``bounded_lsq.trf.trf`` (trf.py:173); ``jac``
+    takes ``(x, f)`` like the reference's wrapped Jacobian."""
+    return _method_entry('trf', fun, jac, x0, lb, ub, ftol, xtol, gtol,
+                         max_nfev, scaling, options)
+
+
+def dogbox(fun, jac, x0, lb, ub, ftol, xtol, gtol, max_nfev, scaling,
+           **options):
+    """Positional signature of ``bounded_lsq.dogbox.dogbox`` (dogbox.py:100)."""
+    return _method_entry('dogbox', fun, jac, x0, lb, ub, ftol, xtol, gtol,
+                         max_nfev, scaling, options)
+
+
+def _method_entry(method, fun, jac, x0, lb, ub, ftol, xtol, gtol, max_nfev,
+                  scaling, options):
+    last_f = {}
+
+    def fun_w(x):
+        f = fun(x)
+        last_f['f'] = f
+        return f
+
+    def jac_w(x):
+        return jac(x, last_f.get('f'))
+
+    res = least_squares(fun_w, x0, jac=jac_w, bounds=(lb, ub), method=method,
+                        ftol=ftol, xtol=xtol, gtol=gtol, max_nfev=max_nfev,
+                        scaling=scaling, options=options)
+    del res['message'], res['success']
+    return res

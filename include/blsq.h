@@ -1,0 +1,155 @@
+/* blsq.h -- C ABI of the B200-native bounded least-squares hot path.
+ *
+ * The reference (nmayorov/bounded-lsq) is pure Python and has no FFI; the seam
+ * this library replaces is the Python call
+ *     least_squares.py:373-379   trf(fun, jac, x0, lb, ub, ftol, xtol, gtol,
+ *                                    max_nfev, scaling) / dogbox(...)
+ * and the helpers those two call (bounds.py, trust_region.py).  Each entry
+ * point cites the reference lines it stands in for.  INTEGRATION.md shows the
+ * ctypes stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - arrays are dense row-major float64 / int32 / int64 / uint8;
+ *   - `stream` is a cudaStream_t passed as void*; nothing synchronises;
+ *   - no allocation, no global state; the caller owns every buffer;
+ *   - return 0 on success, <0 for an invalid argument (BLSQ_E_*), >0 for a
+ *     cudaError_t raised by the launch;
+ *   - bounds are either shared by all problems (bstride = 0, arrays of n) or
+ *     per problem (bstride = n, arrays of B*n).
+ */
+#ifndef BLSQ_H_
+#define BLSQ_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BLSQ_VERSION 100
+
+#define BLSQ_E_BADARG (-1)      /* null pointer / negative size */
+#define BLSQ_E_UNSUPPORTED (-2) /* n outside 1..BLSQ_MAX_BATCHED_N, ... */
+
+#define BLSQ_MAX_BATCHED_N 8
+
+#define BLSQ_METHOD_TRF 0
+#define BLSQ_METHOD_DOGBOX 1
+
+/* per-problem status while a batched solve is in flight; values >= 0 are the
+ * reference's termination codes (least_squares.py:30-37) */
+#define BLSQ_STATUS_RUNNING (-1)
+#define BLSQ_STATUS_ERR_TR_ZERO (-101)    /* trust_region.py:28-29 ValueError */
+#define BLSQ_STATUS_ERR_TR_OUTSIDE (-102) /* trust_region.py:34-35 ValueError */
+
+#define BLSQ_ISTATE_SIZE 8 /* int32 per problem: status, nfev, njev, ... */
+
+int blsq_version(void);
+const char* blsq_error_string(int code);
+
+/* ---- layout queries (host) ------------------------------------------- */
+
+/* Offsets (in doubles) of the fields of one problem's state record:
+ * out[0]=record size, [1]=x, [2]=x_new, [3]=scale, [4]=obj, [5]=Delta,
+ * [6]=optimality (g_norm), [7]=g, [8]=alpha (TRF only, else -1). */
+int blsq_state_layout(int method, int n, int* out_host);
+/* Size in doubles of one linearisation record (packed R, Q^T f, J^T f, f.f) */
+int blsq_lin_record_size(int n);
+
+/* ---- elementwise bound geometry: bit-exact with bounds.py ------------- */
+
+/* bounds.py:24-48 step_size_to_bound, one row of n per problem */
+int blsq_step_size_to_bound(int64_t B, int n, const double* x, const double* d,
+                            const double* lb, const double* ub, int bstride,
+                            double* step, int64_t* hits, void* stream);
+/* bounds.py:51-76 find_active_constraints */
+int blsq_find_active_constraints(int64_t B, int n, const double* x,
+                                 const double* lb, const double* ub,
+                                 int bstride, double rtol, int64_t* mask,
+                                 void* stream);
+/* bounds.py:79-103 make_strictly_feasible */
+int blsq_make_strictly_feasible(int64_t B, int n, const double* x,
+                                const double* lb, const double* ub, int bstride,
+                                double rstep, double* out, void* stream);
+/* bounds.py:106-149 scaling_vector (Coleman-Li v and dv/dx) */
+int blsq_scaling_vector(int64_t B, int n, const double* x, const double* g,
+                        const double* lb, const double* ub, int bstride,
+                        double* v, double* jv, void* stream);
+/* bounds.py:19-21 in_bounds; ok[b] = 1/0 */
+int blsq_in_bounds(int64_t B, int n, const double* x, const double* lb,
+                   const double* ub, int bstride, uint8_t* ok, void* stream);
+/* dogbox.py:9-35 find_intersection; flags bit0 orig_l, bit1 orig_u,
+ * bit2 tr_l, bit3 tr_u */
+int blsq_find_intersection(int64_t B, int n, const double* x, const double* tr,
+                           const double* lb, const double* ub, int bstride,
+                           double* lo, double* hi, uint8_t* flags,
+                           void* stream);
+
+/* ---- 2-point finite differences (least_squares.py:357-365; scipy
+ *      _numdiff._compute_absolute_step/_adjust_scheme_to_bounds) ---------- */
+
+/* For each of A active problems (slot s, problem idx[s] or s when idx is
+ * null): h_i with the bound adjustment, the n perturbed points
+ * Xp[i,s,:] = x + h_i e_i (layout (n, A, n): one (A, n) batch per coordinate,
+ * i.e. one callback call per coordinate like scipy's loop) and
+ * dx[s,i] = (x_i + h_i) - x_i.  rel_step = NaN means diff_step=None. */
+int blsq_fd2_points(int64_t A, const int32_t* idx, int n, const double* x,
+                    const double* lb, const double* ub, int bstride,
+                    double rel_step, double* Xp, double* dx, void* stream);
+
+/* ---- batched solve: init -> [callbacks -> linearise -> round]* -------- */
+
+/* trf.py:201 (x = make_strictly_feasible(x0, rstep=1e-10)) / dogbox.py:131
+ * (x = x0): marks every problem running and writes the first evaluation
+ * point to the state record and to Xnew (B x n). */
+int blsq_init_batched(int method, int64_t B, int n, const double* x0,
+                      const double* lb, const double* ub, int bstride,
+                      double* state, int32_t* istate, double* Xnew,
+                      void* stream);
+
+/* Linearisation at the trial points (trf.py:244,264-274; dogbox.py:170,197):
+ * one QR of [J | f] per problem -> packed R, Q^T f, g = J^T f, f.f.
+ *   jac_mode 0: J is (A, m, n) row-major (analytic Jacobian callback)
+ *   jac_mode 1: Fp_host is a HOST array of n device pointers, Fp_host[i] =
+ *               residuals (A, m) at the i-th perturbed batch of
+ *               blsq_fd2_points, dx (A, n) its denominators;
+ *               J[:, i] = (Fp_i - f) / dx_i is formed in registers (scipy
+ *               _dense_difference) and never materialised.
+ * Slots whose problem is no longer running are skipped. */
+int blsq_linearise_batched(int64_t A, const int32_t* idx, int m, int n,
+                           const double* F, const double* J,
+                           const double* const* Fp_host, const double* dx,
+                           int jac_mode, const int32_t* istate, double* lin,
+                           void* stream);
+
+/* One round of the outer/inner loops for every running problem
+ * (trf.py:238-352 or dogbox.py:164-267): ratio test of the trial in flight,
+ * Delta/alpha update, termination tests, accept, Coleman-Li scaling + SVD of
+ * the hat-space triangle + LM parameter + reflective/gradient candidates
+ * (TRF) or active set + Gauss-Newton/Cauchy + box dogleg (dogbox), and the
+ * next trial point into the state record and Xnew[slot].
+ * Xjac (nullable) receives the point the Jacobian of an accepted step is
+ * evaluated at: for dogbox that is the trial with the coordinates that hit a
+ * bound snapped onto it (dogbox.py:256-261 -- f is taken at x_new, J at the
+ * snapped x); for TRF it equals Xnew.
+ * scaling: n doubles (shared) or null for scaling='jac'. */
+int blsq_round_batched(int method, int64_t A, const int32_t* idx, int m, int n,
+                       const double* lin, const double* x0, const double* lb,
+                       const double* ub, int bstride, const double* scaling,
+                       double ftol, double xtol, double gtol, int max_nfev,
+                       int first, double* state, int32_t* istate, double* Xnew,
+                       double* Xjac, void* stream);
+
+/* dogbox.py:152-154,254: on_bound as the reference's int array (B x n) */
+int blsq_dogbox_on_bound(int64_t B, int n, const int32_t* istate,
+                         int64_t* mask, void* stream);
+
+/* count[0] = number of problems still running (device int32) */
+int blsq_count_running(int64_t B, const int32_t* istate, int32_t* count,
+                       void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BLSQ_H_ */
