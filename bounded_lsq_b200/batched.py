@@ -76,7 +76,7 @@ def _as_f64(t, like, what):
 
 def solve_batched(lib, method, fun, jac, X0, lb, ub, ftol, xtol, gtol,
                   max_nfev, scaling, diff_step=None, check_every=1,
-                  compact_below=0.75, trace=None):
+                  compact_below=0.75, trace=None, timers=None):
     """Run ``method`` ('trf' | 'dogbox') on B problems.
 
     fun(X, idx) -> (A, m); jac is a callable jac(X, idx) -> (A, m, n) or the
@@ -122,6 +122,24 @@ def solve_batched(lib, method, fun, jac, X0, lb, ub, ftol, xtol, gtol,
              ub.data_ptr(), bstride, state.data_ptr(), istate.data_ptr(),
              Xnew.data_ptr(), stream)
 
+    # optional instrumentation (bench.py): CUDA events around every stage
+    def tick():
+        if timers is None or not X0.is_cuda:
+            return None
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
+    def tock(kind, e0, running):
+        if e0 is None:
+            return
+        e1 = torch.cuda.Event(enable_timing=True)
+        e1.record()
+        timers.setdefault(kind, []).append((e0, e1, running))
+    if timers is not None:
+        timers["shape"] = (n, None, LS, S)
+    nrun = B
+
     idx = None          # int64 for torch gathers
     idx32 = None        # int32 copy handed to the kernels
     A = B
@@ -132,6 +150,7 @@ def solve_batched(lib, method, fun, jac, X0, lb, ub, ftol, xtol, gtol,
     while A > 0:
         Xa = Xnew[:A]
         Xj = Xa if (Xjac is None or first) else Xjac[:A]
+        t0 = tick()
         F = _as_f64(fun(Xa, idx), X0, "fun")
         if F.dim() != 2 or F.shape[0] != A:
             raise RuntimeError("batched `fun` must return an (A, m) tensor, "
@@ -152,9 +171,12 @@ def solve_batched(lib, method, fun, jac, X0, lb, ub, ftol, xtol, gtol,
                     "Inconsistent dimensions between the returns of `fun` "
                     "and `jac` on the first iteration.")
             J = J.contiguous()
+            tock("callbacks", t0, nrun)
+            t0 = tick()
             lib.call("blsq_linearise_batched", A, ip, m, n, F.data_ptr(),
                      J.data_ptr(), None, None, 0, istate.data_ptr(),
                      lin.data_ptr(), stream)
+            tock("linearise", t0, nrun)
         else:
             Xpa = Xp.view(-1)[: n * A * n].view(n, A, n)
             lib.call("blsq_fd2_points", A, ip, n, Xj.data_ptr(), lb.data_ptr(),
@@ -168,14 +190,21 @@ def solve_batched(lib, method, fun, jac, X0, lb, ub, ftol, xtol, gtol,
                     raise RuntimeError("`fun` changed its output shape")
                 Fp.append(Fi)
             plist = (C.c_void_p * n)(*[t.data_ptr() for t in Fp])
+            tock("callbacks", t0, nrun)
+            t0 = tick()
             lib.call("blsq_linearise_batched", A, ip, m, n, F.data_ptr(), None,
                      C.cast(plist, C.c_void_p), dx.data_ptr(), 1,
                      istate.data_ptr(), lin.data_ptr(), stream)
+            tock("linearise", t0, nrun)
+        t0 = tick()
         lib.call("blsq_round_batched", meth, A, ip, m, n, lin.data_ptr(),
                  X0.data_ptr(), lb.data_ptr(), ub.data_ptr(), bstride, sc_ptr,
                  float(ftol), float(xtol), float(gtol), max_nfev, first,
                  state.data_ptr(), istate.data_ptr(), Xnew.data_ptr(),
                  None if Xjac is None else Xjac.data_ptr(), stream)
+        tock("round", t0, nrun)
+        if timers is not None:
+            timers["shape"] = (n, m, LS, S)
         launches += 2
         first = 0
         rounds += 1
@@ -222,3 +251,36 @@ def solve_batched(lib, method, fun, jac, X0, lb, ub, ftol, xtol, gtol,
         optimality=state[:, lay["gnorm"]].clone(), active_mask=mask,
         nfev=istate[:, 1].to(torch.int64), njev=istate[:, 2].to(torch.int64),
         status=status, m=m, rounds=rounds, kernel_launches=launches)
+
+
+def summarize_timers(timers):
+    """Per-kernel totals from the events collected with ``timers=``.
+
+    Algorithmic bytes per running problem (DESIGN.md "Roofline accounting"):
+      linearise  8*m*(n+1) read ([J | f]) + 8*LS written (the record)
+      round      8*LS read + 2*8*S state read/write + 2*32 istate + 8*n x_new
+    """
+    if not timers or "linearise" not in timers:
+        return {}
+    n, m, LS, S = timers["shape"]
+    per = {"linearise": 8 * m * (n + 1) + 8 * LS,
+           "round": 8 * LS + 16 * S + 64 + 8 * n}
+    out = {}
+    tot = {}
+    for kind in ("callbacks", "linearise", "round"):
+        ev = timers.get(kind, [])
+        ms = [a.elapsed_time(b) for a, b, _ in ev]
+        tot[kind] = sum(ms)
+        if kind in per and ms:
+            byts = sum(r * per[kind] for _, _, r in ev)
+            out[kind] = dict(launches=len(ms), total_ms=tot[kind],
+                             avg_ms=tot[kind] / len(ms),
+                             gbs=byts / (tot[kind] * 1e-3) / 1e9,
+                             bytes_per_problem=per[kind])
+    kt = tot["linearise"] + tot["round"]
+    for kind in ("linearise", "round"):
+        if kind in out:
+            out[kind]["share"] = tot[kind] / kt if kt else None
+    out["callbacks_ms"] = tot["callbacks"]
+    out["kernels_ms"] = kt
+    return out

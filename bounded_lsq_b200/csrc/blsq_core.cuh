@@ -51,12 +51,12 @@ BLSQ_HD double dnan() { return HUGE_VAL - HUGE_VAL; }
 BLSQ_HD double np_max(double a, double b) {
     if (a != a) return a;
     if (b != b) return b;
-    return a > b ? a : b;
+    return a >= b ? a : b;          // ties keep the first operand, like NumPy
 }
 BLSQ_HD double np_min(double a, double b) {
     if (a != a) return a;
     if (b != b) return b;
-    return a < b ? a : b;
+    return a <= b ? a : b;
 }
 BLSQ_HD int isign(double v) { return (v > 0) - (v < 0); }
 BLSQ_HD bool finite_d(double v) { return fabs(v) <= 1.79769313486231570815e+308; }
@@ -91,7 +91,7 @@ BLSQ_HD double step_size_to_bound(const double* x, const double* d,
             t[i] = dinf();
         }
         if (t[i] != t[i]) has_nan = true;
-        if (t[i] < tmin) tmin = t[i];
+        if (!(tmin < t[i])) tmin = t[i];   // NumPy: ties take the later element
     }
     if (has_nan) tmin = dnan();          // np.min propagates NaN
     if (hits) {
@@ -794,7 +794,7 @@ BLSQ_HD double step_to_box(const double* x, const double* d, const double* lo,
         else
             t[i] = dinf();
         if (t[i] != t[i]) has_nan = true;
-        if (t[i] < tmin) tmin = t[i];
+        if (!(tmin < t[i])) tmin = t[i];   // NumPy: ties take the later element
     }
     if (has_nan) tmin = dnan();
     BLSQ_UNROLL

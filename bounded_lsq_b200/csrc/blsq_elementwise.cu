@@ -44,7 +44,10 @@ __global__ void step_size_kernel(int64_t B, int n, int G,
     int lane = (int)(t % G);
     bool valid = b < B;
     // pass 1: row minimum (NaN-propagating like np.min)
+    // NumPy's sequential minimum keeps the LATER element on ties, which
+    // decides the sign of a zero step; carry the index to reproduce it
     double tmin = dinf();
+    int imin = -1;
     bool has_nan = false;
     if (valid) {
         for (int i = lane; i < n; i += G) {
@@ -56,13 +59,14 @@ __global__ void step_size_kernel(int64_t B, int n, int G,
                             (ub[b * bstride + i] - xi) / di);
             }
             if (ti != ti) has_nan = true;
-            if (ti < tmin) tmin = ti;
+            if (!(tmin < ti)) { tmin = ti; imin = i; }
         }
     }
     for (int off = G >> 1; off > 0; off >>= 1) {
         double o = __shfl_xor_sync(0xffffffffu, tmin, off, 32);
+        int oi = __shfl_xor_sync(0xffffffffu, imin, off, 32);
         bool on = __shfl_xor_sync(0xffffffffu, (int)has_nan, off, 32);
-        if (o < tmin) tmin = o;
+        if (o < tmin || (o == tmin && oi > imin)) { tmin = o; imin = oi; }
         has_nan = has_nan || on;
     }
     if (has_nan) tmin = dnan();

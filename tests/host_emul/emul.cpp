@@ -117,7 +117,7 @@ int blsq_step_size_to_bound(int64_t B, int n, const double* x, const double* d,
                 t[i] = np_max((lb[b * bs + i] - x[b * n + i]) / di,
                               (ub[b * bs + i] - x[b * n + i]) / di);
             if (t[i] != t[i]) has_nan = true;
-            if (t[i] < tmin) tmin = t[i];
+            if (!(tmin < t[i])) tmin = t[i];
         }
         if (has_nan) tmin = dnan();
         step[b] = tmin;

@@ -1,0 +1,107 @@
+"""GPU suite (B200): the parity tests proper.  Every case goes through the C
+ABI of bounded_lsq_b200/libblsq_b200.so on cuda:0 and is compared with the
+golden vectors written by the unmodified reference / with the oracle."""
+import numpy as np
+import pytest
+import torch
+
+import cases
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from bounded_lsq_b200 import get_lib
+    return get_lib()
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda:0")
+
+
+def test_helpers_bit_exact(lib, dev):
+    assert cases.check_helpers_bit_exact(lib, dev) > 50
+
+
+def test_helpers_batched_rows(lib, dev):
+    cases.check_helpers_batched_rows(lib, dev)
+
+
+@pytest.mark.parametrize("name", ["c2_trf_exact", "c2_dogbox_exact"])
+def test_golden_exact_jac(lib, dev, name):
+    s = cases.check_golden_exact_jac(lib, dev, name)
+    print(name, s)
+
+
+@pytest.mark.parametrize("name", ["c3_dogbox_2point", "c3_trf_2point"])
+def test_golden_fd_jac(lib, dev, name):
+    s = cases.check_golden_fd_jac(lib, dev, name)
+    print(name, s)
+
+
+def test_compaction_invariance(lib, dev):
+    cases.check_compaction_invariance(lib, dev)
+
+
+def test_per_problem_bounds(lib, dev):
+    cases.check_per_problem_bounds(lib, dev)
+
+
+def test_corpus_single(lib, dev):
+    st = cases.check_corpus_single(lib, dev)
+    print(st)
+    assert st["exact_status"] >= 60
+
+
+def test_oracle_side_by_side_fresh_seed(lib, dev):
+    """Problems NOT in the golden files: oracle run here on the host CPU."""
+    from oracle import blsq_oracle as orc
+    from bounded_lsq_b200 import least_squares_batched, PerProblem
+    from bounded_lsq_b200.synthetic import ExpDecay2
+    model = ExpDecay2()
+    B = 96
+    _, y = model.make_data(B, seed=777)
+    X0 = cases.T(np.tile(model.x0, (B, 1)), dev)
+    for method in ("trf", "dogbox"):
+        res = least_squares_batched(
+            model.fun_t, X0, jac=model.jac_t, bounds=(model.lb, model.ub),
+            method=method, args=(PerProblem(cases.T(y, dev)),))
+        x = res.x.cpu().numpy()
+        for b in range(B):
+            ref = orc.least_squares(model.fun_np, model.x0, jac=model.jac_np,
+                                    bounds=(model.lb, model.ub), method=method,
+                                    args=(y[b],))
+            assert ref.status == int(res.status[b])
+            assert ref.nfev == int(res.nfev[b])
+            assert np.allclose(x[b], ref.x, rtol=1e-8, atol=0)
+            assert cases.bits(res.active_mask[b].cpu().numpy(),
+                              np.asarray(ref.active_mask))
+
+
+def test_large_batch_properties(lib, dev):
+    """Size-independent properties at a size the oracle cannot cover: every
+    fit ends feasible, with a termination status, and problems that are exact
+    copies of each other end bit-identical wherever they sit in the batch."""
+    from bounded_lsq_b200 import least_squares_batched, PerProblem
+    from bounded_lsq_b200.synthetic import ExpDecay2
+    model = ExpDecay2()
+    B = 200_000
+    _, y = model.make_data(4096, seed=5)
+    reps = B // 4096 + 1
+    yb = cases.T(np.tile(y, (reps, 1))[:B], dev)
+    X0 = cases.T(np.tile(model.x0, (B, 1)), dev)
+    res = least_squares_batched(model.fun_t, X0, jac=model.jac_t,
+                                bounds=(model.lb, model.ub), method='trf',
+                                args=(PerProblem(yb),))
+    lb = cases.T(model.lb, dev)
+    ub = cases.T(model.ub, dev)
+    assert bool(((res.x >= lb) & (res.x <= ub)).all())
+    assert bool((res.status >= 0).all())
+    assert float((res.status > 0).double().mean()) > 0.99
+    k = (B // 4096) * 4096
+    xs = res.x[:k].reshape(-1, 4096, 4)
+    assert bool((xs == xs[0:1]).all())
+    ns = res.nfev[:k].reshape(-1, 4096)
+    assert bool((ns == ns[0:1]).all())
