@@ -37,6 +37,8 @@ SIGNATURES = {
                            _d, _d, _d, _i, _i, _p, _p, _p, _p, _p],
     "blsq_dogbox_on_bound": [_l, _i, _p, _p, _p],
     "blsq_count_running": [_l, _p, _p, _p],
+    "blsq_model_expdecay2": [_l, _p, _i, _p, _p, _p, _p, _p, _p],
+    "blsq_model_gausspeak": [_l, _p, _i, _p, _p, _p, _p, _p],
     "blsq_tall_workspace_size": [_l, _i],
     "blsq_tsqr_local": [_l, _i, _p, _p, _p, _p, _p],
     "blsq_tall_round": [_i, _i, _i, _l, _p, _p, _p, _p, _p, _d, _d, _d, _i,

@@ -55,13 +55,22 @@ class BatchedCallbacks:
         self.args, self.kwargs = tuple(args), dict(kwargs or {})
         self.B = B
 
-    def f(self, X, idx):
+    def _call(self, fn, X, idx):
+        if getattr(fn, "blsq_indexed", False):
+            # indexed protocol: raw per-problem tensors + the active ids
+            a = tuple(v.tensor if isinstance(v, PerProblem) else v
+                      for v in self.args)
+            k = {n: (v.tensor if isinstance(v, PerProblem) else v)
+                 for n, v in self.kwargs.items()}
+            return fn(X, idx, *a, **k)
         a, k = _gather_args(self.args, self.kwargs, idx)
-        return self.fun(X, *a, **k)
+        return fn(X, *a, **k)
+
+    def f(self, X, idx):
+        return self._call(self.fun, X, idx)
 
     def j(self, X, idx):
-        a, k = _gather_args(self.args, self.kwargs, idx)
-        return self.jac(X, *a, **k)
+        return self._call(self.jac, X, idx)
 
 
 def _as_f64(t, like, what):

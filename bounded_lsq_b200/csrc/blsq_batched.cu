@@ -30,10 +30,31 @@ using namespace blsq;
 
 namespace {
 
-// rows per lane held in registers by lin_kernel
-template <int N> struct LinCfg { static constexpr int RPL = (N <= 4) ? 8 : 4; };
+// ---- build knobs (tools/kbench.py explores them) --------------------------
+#ifndef BLSQ_LIN_THREADS
+#define BLSQ_LIN_THREADS 128
+#endif
+#ifndef BLSQ_LIN_MINB
+#define BLSQ_LIN_MINB 4
+#endif
+#ifndef BLSQ_ROUND_THREADS
+#define BLSQ_ROUND_THREADS 128
+#endif
+#ifndef BLSQ_ROUND_MINB
+#define BLSQ_ROUND_MINB 4
+#endif
 
-__device__ __forceinline__ double group_sum(double v, int G) {
+// rows per lane held in registers by lin_kernel
+#ifndef BLSQ_RPL_SMALL
+#define BLSQ_RPL_SMALL 8
+#endif
+template <int N> struct LinCfg {
+    static constexpr int RPL = (N <= 4) ? BLSQ_RPL_SMALL : 4;
+};
+
+template <int G>
+__device__ __forceinline__ double group_sum(double v) {
+#pragma unroll
     for (int off = G >> 1; off > 0; off >>= 1)
         v += __shfl_xor_sync(0xffffffffu, v, off, 32);
     return v;
@@ -41,11 +62,13 @@ __device__ __forceinline__ double group_sum(double v, int G) {
 
 template <int N> struct PtrList { const double* p[N]; };
 
+// One group of G lanes (G = 8, 16 or 32) per problem; row (base + s*G + lane)
+// of the current chunk sits in a[s][*] of that lane.
 // MODE 0: analytic J (A, m, n).  MODE 1: finite differences, Fpert.p[i] is
 // F at the i-th perturbed batch, (A, m); dx is (A, n).
-template <int N, int MODE>
-__global__ void __launch_bounds__(256)
-lin_kernel(int64_t A, const int32_t* __restrict__ idx, int m, int G,
+template <int N, int G, int MODE>
+__global__ void __launch_bounds__(BLSQ_LIN_THREADS, BLSQ_LIN_MINB)
+lin_kernel(int64_t A, const int32_t* __restrict__ idx, int m,
            const double* __restrict__ F, const double* __restrict__ J,
            PtrList<N> Fpert, const double* __restrict__ dx,
            const int32_t* __restrict__ istate, double* __restrict__ lin) {
@@ -61,6 +84,7 @@ lin_kernel(int64_t A, const int32_t* __restrict__ idx, int m, int G,
         valid = istate[pid * IS_SIZE + IS_STATUS] == ST_RUNNING;
     }
     if (!__any_sync(0xffffffffu, valid)) return;
+    const bool all_valid = __all_sync(0xffffffffu, valid);
 
     const double* Fp = F + slot * (int64_t)m;
     const double* Jp = (MODE == 0) ? J + slot * (int64_t)m * N : nullptr;
@@ -68,28 +92,27 @@ lin_kernel(int64_t A, const int32_t* __restrict__ idx, int m, int G,
     if (MODE == 1) {
 #pragma unroll
         for (int j = 0; j < N; j++)
-            dxj[j] = valid ? dx[slot * N + j] : 1.0;
+            dxj[j] = valid ? 1.0 / dx[slot * N + j] : 1.0;   // reciprocal once
     }
 
-    double a[RPL + 1][C];
-    double r[N][C];
+    double a[RPL + 1][C];        // a[RPL] = carried row of the running triangle
+    double myrow[C];             // row `lane` (< N) of the triangle, [.. | qtf]
     double gp[N], objp = 0.0;
 #pragma unroll
     for (int j = 0; j < N; j++) gp[j] = 0.0;
 #pragma unroll
-    for (int k = 0; k < N; k++) {
-#pragma unroll
-        for (int j = 0; j < C; j++) r[k][j] = 0.0;
-    }
+    for (int j = 0; j < C; j++) { myrow[j] = 0.0; a[RPL][j] = 0.0; }
+    const bool multi = m > G * RPL;
 
     for (int base = 0; base < m; base += G * RPL) {
-        // ---- load this chunk: row (base + s*G + lane) -> a[s][*] ----
+        const bool full = all_valid && (base + G * RPL <= m);   // warp-uniform
+        // ---- load this chunk ----
 #pragma unroll
         for (int s = 0; s < RPL; s++) {
             int row = base + s * G + lane;
-            bool ok = valid && row < m;
-            if (MODE == 0) {
-                if (ok) {
+            bool ok = full || (valid && row < m);
+            if (ok) {
+                if (MODE == 0) {
                     const double* rp = Jp + (int64_t)row * N;
                     if (N % 2 == 0) {
 #pragma unroll
@@ -102,34 +125,27 @@ lin_kernel(int64_t A, const int32_t* __restrict__ idx, int m, int G,
 #pragma unroll
                         for (int j = 0; j < N; j++) a[s][j] = __ldcs(rp + j);
                     }
-                    a[s][N] = __ldcs(Fp + row);
                 } else {
-#pragma unroll
-                    for (int j = 0; j < C; j++) a[s][j] = 0.0;
-                }
-            } else {
-                if (ok) {
-                    double f0 = __ldcs(Fp + row);
-                    a[s][N] = f0;
 #pragma unroll
                     for (int j = 0; j < N; j++)
                         a[s][j] = __ldcs(Fpert.p[j] + slot * (int64_t)m + row);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < C; j++) a[s][j] = 0.0;
                 }
+                a[s][N] = __ldcs(Fp + row);
+            } else {
+#pragma unroll
+                for (int j = 0; j < C; j++) a[s][j] = 0.0;
             }
         }
         if (MODE == 1) {
-            // scipy _dense_difference: J[:, i] = (f(x + h_i e_i) - f0) / dx_i
+            // scipy _dense_difference: J[:, i] = (f(x + h_i e_i) - f0) / dx_i,
+            // as a multiplication by 1/dx_i (<= 1 ulp from the quotient, far
+            // below the 1e-8 truncation noise of the difference itself);
+            // rows that were not loaded hold zeros: (0 - 0) * c = 0
 #pragma unroll
             for (int s = 0; s < RPL; s++) {
-                int row = base + s * G + lane;
-                if (valid && row < m) {
 #pragma unroll
-                    for (int j = 0; j < N; j++)
-                        a[s][j] = (a[s][j] - a[s][N]) / dxj[j];
-                }
+                for (int j = 0; j < N; j++)
+                    a[s][j] = (a[s][j] - a[s][N]) * dxj[j];
             }
         }
         // ---- g = J^T f and f.f on the raw rows (trf.py:244, 229) ----
@@ -140,14 +156,9 @@ lin_kernel(int64_t A, const int32_t* __restrict__ idx, int m, int G,
             objp = fma(a[s][N], a[s][N], objp);
         }
         // ---- carry: row k of the running triangle lives on lane k ----
+        if (multi) {
 #pragma unroll
-        for (int j = 0; j < C; j++) a[RPL][j] = 0.0;
-#pragma unroll
-        for (int k = 0; k < N; k++) {
-            if (lane == k) {
-#pragma unroll
-                for (int j = k; j < C; j++) a[RPL][j] = r[k][j];
-            }
+            for (int j = 0; j < C; j++) a[RPL][j] = (lane < N) ? myrow[j] : 0.0;
         }
         // ---- modified Gram-Schmidt on the stacked (carry + chunk) rows ----
 #pragma unroll
@@ -157,25 +168,34 @@ lin_kernel(int64_t A, const int32_t* __restrict__ idx, int m, int G,
             for (int j = k; j < C; j++) {
                 double acc = 0.0;
 #pragma unroll
-                for (int s = 0; s <= RPL; s++) acc = fma(a[s][k], a[s][j], acc);
-                dts[j] = group_sum(acc, G);
+                for (int s = 0; s < RPL; s++) acc = fma(a[s][k], a[s][j], acc);
+                if (multi) acc = fma(a[RPL][k], a[RPL][j], acc);
+                dts[j] = group_sum<G>(acc);
             }
-            double dk = dts[k];
-            double rkk = sqrt(dk);
-            r[k][k] = rkk;
+            const double dk = dts[k];
+            const bool pos = dk > 0.0;
+            const double rkk = sqrt(dk);
+            const double inv_dk = pos ? 1.0 / dk : 0.0;
+            const double inv_rkk = rkk * inv_dk;           // 1/sqrt(dk)
+            if (lane == k) {
+#pragma unroll
+                for (int j = 0; j < C; j++) myrow[j] = 0.0;
+                myrow[k] = rkk;
+            }
 #pragma unroll
             for (int j = k + 1; j < C; j++) {
-                double coef = (dk > 0.0) ? dts[j] / dk : 0.0;
-                r[k][j] = (dk > 0.0) ? dts[j] / rkk : 0.0;
+                const double coef = dts[j] * inv_dk;
+                if (lane == k) myrow[j] = dts[j] * inv_rkk;
 #pragma unroll
-                for (int s = 0; s <= RPL; s++)
+                for (int s = 0; s < RPL; s++)
                     a[s][j] = fma(-coef, a[s][k], a[s][j]);
+                if (multi) a[RPL][j] = fma(-coef, a[RPL][k], a[RPL][j]);
             }
         }
     }
 #pragma unroll
-    for (int j = 0; j < N; j++) gp[j] = group_sum(gp[j], G);
-    objp = group_sum(objp, G);
+    for (int j = 0; j < N; j++) gp[j] = group_sum<G>(gp[j]);
+    objp = group_sum<G>(objp);
 
     if (valid) {
         double* out = lin + slot * (int64_t)L::SIZE;
@@ -184,8 +204,8 @@ lin_kernel(int64_t A, const int32_t* __restrict__ idx, int m, int G,
         for (int k = 0; k < N; k++) {
             if (lane == k) {
 #pragma unroll
-                for (int j = k; j < N; j++) out[L::R + tri_index<N>(k, j)] = r[k][j];
-                out[L::QTF + k] = r[k][N];
+                for (int j = k; j < N; j++) out[L::R + tri_index<N>(k, j)] = myrow[j];
+                out[L::QTF + k] = myrow[N];
                 out[L::G + k] = gp[k];
             }
         }
@@ -194,7 +214,7 @@ lin_kernel(int64_t A, const int32_t* __restrict__ idx, int m, int G,
 }
 
 template <int N, int METHOD>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(BLSQ_ROUND_THREADS, BLSQ_ROUND_MINB)
 round_kernel(int64_t A, const int32_t* __restrict__ idx,
              const double* __restrict__ lin, const double* __restrict__ x0,
              const double* __restrict__ lb, const double* __restrict__ ub,
@@ -220,8 +240,17 @@ round_kernel(int64_t A, const int32_t* __restrict__ idx,
     if (ist[IS_STATUS] != ST_RUNNING) return;
     double st[SS];
     double* sp = state + pid * (int64_t)SS;
+    if (SS % 2 == 0) {
 #pragma unroll
-    for (int i = 0; i < SS; i++) st[i] = sp[i];
+        for (int i = 0; i < SS; i += 2) {
+            double2 t = *reinterpret_cast<const double2*>(sp + i);
+            st[i] = t.x;
+            st[i + 1] = t.y;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < SS; i++) st[i] = sp[i];
+    }
     double ln[L::SIZE];
     const double* lp = lin + slot * (int64_t)L::SIZE;
 #pragma unroll
@@ -240,8 +269,14 @@ round_kernel(int64_t A, const int32_t* __restrict__ idx,
     else
         go = dogbox_round<N>(st, ist, ln, x0 + pid * N, lb + pid * bstride,
                              ub + pid * bstride, sc, P, first);
+    if (SS % 2 == 0) {
 #pragma unroll
-    for (int i = 0; i < SS; i++) sp[i] = st[i];
+        for (int i = 0; i < SS; i += 2)
+            *reinterpret_cast<double2*>(sp + i) = make_double2(st[i], st[i + 1]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < SS; i++) sp[i] = st[i];
+    }
     *reinterpret_cast<int4*>(ip) = make_int4(ist[0], ist[1], ist[2], ist[3]);
     *reinterpret_cast<int4*>(ip + 4) = make_int4(ist[4], ist[5], ist[6], ist[7]);
     if (go) {
@@ -308,25 +343,38 @@ __global__ void count_running_kernel(int64_t B,
     if ((threadIdx.x & 31) == 0 && bal) atomicAdd(count, __popc(bal));
 }
 
+template <int N, int G>
+int launch_lin_g(int64_t A, const int32_t* idx, int m, const double* F,
+                 const double* J, const PtrList<N>& pl, const double* dx,
+                 int jac_mode, const int32_t* istate, double* lin,
+                 cudaStream_t s) {
+    int64_t threads = A * G;
+    int64_t blocks = (threads + BLSQ_LIN_THREADS - 1) / BLSQ_LIN_THREADS;
+    if (blocks > 0x7fffffff) return BLSQ_E_UNSUPPORTED;
+    if (jac_mode == 0)
+        lin_kernel<N, G, 0><<<(unsigned)blocks, BLSQ_LIN_THREADS, 0, s>>>(
+            A, idx, m, F, J, pl, dx, istate, lin);
+    else
+        lin_kernel<N, G, 1><<<(unsigned)blocks, BLSQ_LIN_THREADS, 0, s>>>(
+            A, idx, m, F, J, pl, dx, istate, lin);
+    BLSQ_LAUNCH_CHECK();
+    return 0;
+}
+
 template <int N>
 int launch_lin(int64_t A, const int32_t* idx, int m, const double* F,
                const double* J, const double* const* Fp_host, const double* dx,
                int jac_mode, const int32_t* istate, double* lin,
                cudaStream_t s) {
     constexpr int RPL = LinCfg<N>::RPL;
-    int G = 8;
-    while (G < 32 && G * RPL < m) G <<= 1;
-    int64_t threads = A * G;
-    int64_t blocks = (threads + 255) / 256;
-    if (blocks > 0x7fffffff) return BLSQ_E_UNSUPPORTED;
     PtrList<N> pl;
     for (int j = 0; j < N; j++) pl.p[j] = (jac_mode == 1) ? Fp_host[j] : nullptr;
-    if (jac_mode == 0)
-        lin_kernel<N, 0><<<(unsigned)blocks, 256, 0, s>>>(A, idx, m, G, F, J, pl, dx, istate, lin);
-    else
-        lin_kernel<N, 1><<<(unsigned)blocks, 256, 0, s>>>(A, idx, m, G, F, J, pl, dx, istate, lin);
-    BLSQ_LAUNCH_CHECK();
-    return 0;
+    // smallest lane group whose registers hold all m rows (else 32 + chunks)
+    if (m <= 8 * RPL)
+        return launch_lin_g<N, 8>(A, idx, m, F, J, pl, dx, jac_mode, istate, lin, s);
+    if (m <= 16 * RPL)
+        return launch_lin_g<N, 16>(A, idx, m, F, J, pl, dx, jac_mode, istate, lin, s);
+    return launch_lin_g<N, 32>(A, idx, m, F, J, pl, dx, jac_mode, istate, lin, s);
 }
 
 template <int N>
@@ -335,13 +383,13 @@ int launch_round(int method, int64_t A, const int32_t* idx, const double* lin,
                  int bstride, const double* scaling, SolveParams P, int first,
                  double* state, int32_t* istate, double* Xnew, double* Xjac,
                  cudaStream_t s) {
-    int64_t blocks = (A + 127) / 128;
+    int64_t blocks = (A + BLSQ_ROUND_THREADS - 1) / BLSQ_ROUND_THREADS;
     if (blocks > 0x7fffffff) return BLSQ_E_UNSUPPORTED;
     if (method == BLSQ_METHOD_TRF)
-        round_kernel<N, BLSQ_METHOD_TRF><<<(unsigned)blocks, 128, 0, s>>>(
+        round_kernel<N, BLSQ_METHOD_TRF><<<(unsigned)blocks, BLSQ_ROUND_THREADS, 0, s>>>(
             A, idx, lin, x0, lb, ub, bstride, scaling, P, first, state, istate, Xnew, Xjac);
     else
-        round_kernel<N, BLSQ_METHOD_DOGBOX><<<(unsigned)blocks, 128, 0, s>>>(
+        round_kernel<N, BLSQ_METHOD_DOGBOX><<<(unsigned)blocks, BLSQ_ROUND_THREADS, 0, s>>>(
             A, idx, lin, x0, lb, ub, bstride, scaling, P, first, state, istate, Xnew, Xjac);
     BLSQ_LAUNCH_CHECK();
     return 0;
@@ -349,6 +397,14 @@ int launch_round(int method, int64_t A, const int32_t* idx, const double* lin,
 
 }  // namespace
 
+#ifdef BLSQ_ONLY_N46      /* quick builds for tools/build_variants.sh */
+#define BLSQ_DISPATCH_N(n, CALL)          \
+    switch (n) {                          \
+        case 4: { constexpr int N_ = 4; CALL; } break; \
+        case 6: { constexpr int N_ = 6; CALL; } break; \
+        default: return BLSQ_E_UNSUPPORTED; \
+    }
+#else
 #define BLSQ_DISPATCH_N(n, CALL)          \
     switch (n) {                          \
         case 1: { constexpr int N_ = 1; CALL; } break; \
@@ -361,6 +417,7 @@ int launch_round(int method, int64_t A, const int32_t* idx, const double* lin,
         case 8: { constexpr int N_ = 8; CALL; } break; \
         default: return BLSQ_E_UNSUPPORTED; \
     }
+#endif
 
 extern "C" {
 

@@ -170,13 +170,13 @@ BLSQ_HD void phi_and_derivative(double alpha, const double* suf,
     dphi = -dd / pn;
 }
 
-// trust_region.py:56-152.  V is row-major N x N, column j = right singular
-// vector j; suf = s * (U^T f).  The singular values need not be sorted: the
+// trust_region.py:56-152.  Vt is row-major N x N, ROW j = right singular
+// vector j (i.e. V transposed); suf = s * (U^T f).  The singular values need not be sorted: the
 // rank test uses min/max, everything else is a sum over j.  alpha is the
 // warm start on entry and the LM parameter on exit.
 template <int N>
 BLSQ_HD void solve_lsq_trust_region(int m, const double* suf, const double* s,
-                                    const double* V, double Delta,
+                                    const double* Vt, double Delta,
                                     double& alpha, double* p) {
     double smin = s[0], smax = s[0];
     BLSQ_UNROLL
@@ -190,7 +190,12 @@ BLSQ_HD void solve_lsq_trust_region(int m, const double* suf, const double* s,
         BLSQ_UNROLL
         for (int j = 0; j < N; j++) w[j] = (suf[j] / s[j]) / s[j];
         BLSQ_UNROLL
-        for (int i = 0; i < N; i++) p[i] = -dot<N>(V + i * N, w);
+        for (int i = 0; i < N; i++) {
+            double acc = 0.0;
+            BLSQ_UNROLL
+            for (int j = 0; j < N; j++) acc = fma(Vt[j * N + i], w[j], acc);
+            p[i] = -acc;
+        }
         if (norm2<N>(p) <= Delta) { alpha = 0.0; return; }
     }
     double hi = norm2<N>(suf) / Delta;
@@ -220,7 +225,12 @@ BLSQ_HD void solve_lsq_trust_region(int m, const double* suf, const double* s,
     BLSQ_UNROLL
     for (int j = 0; j < N; j++) w[j] = suf[j] / (s[j] * s[j] + alpha);
     BLSQ_UNROLL
-    for (int i = 0; i < N; i++) p[i] = -dot<N>(V + i * N, w);
+    for (int i = 0; i < N; i++) {
+        double acc = 0.0;
+        BLSQ_UNROLL
+        for (int j = 0; j < N; j++) acc = fma(Vt[j * N + i], w[j], acc);
+        p[i] = -acc;
+    }
     if (phi > 0) {
         double sc = Delta / norm2<N>(p);
         BLSQ_UNROLL
@@ -252,17 +262,24 @@ BLSQ_HD void tri_matvec(const double* R, const double* s, double* y) {
     }
 }
 
+BLSQ_HD double rsqrt_d(double x) {
+#if defined(__CUDA_ARCH__)
+    return rsqrt(x);
+#else
+    return 1.0 / sqrt(x);
+#endif
+}
+
 // One-sided (Hestenes) Jacobi SVD of the N x N matrix A (row-major, in
-// place): on exit the columns of A are U_j * s_j, V holds the right singular
-// vectors as columns.  High relative accuracy; order of singular values is
-// whatever falls out (callers do not depend on it).
+// place), run on the ROWS of A, i.e. on the columns of A^T.  For the upper
+// triangles this is fed, A^T is lower triangular, which is the orientation in
+// which one-sided Jacobi converges fastest (Drmac & Veselic).  With
+//   A = U S V^T :  rows of A  ->  s_j * v_j^T   (right singular vectors)
+//                  b          ->  U^T b         (same rotations applied to b)
+// so neither U nor V is accumulated.  High relative accuracy; the order of
+// the singular values is whatever falls out (callers do not depend on it).
 template <int N>
-BLSQ_HD void jacobi_svd(double* A, double* V) {
-    BLSQ_UNROLL
-    for (int i = 0; i < N; i++) {
-        BLSQ_UNROLL
-        for (int j = 0; j < N; j++) V[i * N + j] = (i == j) ? 1.0 : 0.0;
-    }
+BLSQ_HD void jacobi_rows(double* A, double* b) {
     if (N == 1) return;
     for (int sweep = 0; sweep < 40; sweep++) {
         bool rotated = false;
@@ -273,27 +290,27 @@ BLSQ_HD void jacobi_svd(double* A, double* V) {
                 double al = 0.0, be = 0.0, ga = 0.0;
                 BLSQ_UNROLL
                 for (int i = 0; i < N; i++) {
-                    double ap = A[i * N + p], aq = A[i * N + q];
+                    double ap = A[p * N + i], aq = A[q * N + i];
                     al = fma(ap, ap, al);
                     be = fma(aq, aq, be);
                     ga = fma(ap, aq, ga);
                 }
-                if (ga == 0.0 || fabs(ga) <= EPS * sqrt(al * be)) continue;
+                if (ga == 0.0 || ga * ga <= (EPS * EPS) * (al * be)) continue;
                 rotated = true;
                 double zeta = (be - al) / (2.0 * ga);
                 double t = copysign(1.0, zeta) /
-                           (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-                double c = 1.0 / sqrt(1.0 + t * t);
+                           (fabs(zeta) + sqrt(fma(zeta, zeta, 1.0)));
+                double c = rsqrt_d(fma(t, t, 1.0));
                 double sn = c * t;
                 BLSQ_UNROLL
                 for (int i = 0; i < N; i++) {
-                    double ap = A[i * N + p], aq = A[i * N + q];
-                    A[i * N + p] = fma(c, ap, -(sn * aq));
-                    A[i * N + q] = fma(sn, ap, c * aq);
-                    double vp = V[i * N + p], vq = V[i * N + q];
-                    V[i * N + p] = fma(c, vp, -(sn * vq));
-                    V[i * N + q] = fma(sn, vp, c * vq);
+                    double ap = A[p * N + i], aq = A[q * N + i];
+                    A[p * N + i] = fma(c, ap, -(sn * aq));
+                    A[q * N + i] = fma(sn, ap, c * aq);
                 }
+                double bp = b[p], bq = b[q];
+                b[p] = fma(c, bp, -(sn * bq));
+                b[q] = fma(sn, bp, c * bq);
             }
         }
         if (!rotated) break;
@@ -305,11 +322,12 @@ BLSQ_HD void jacobi_svd(double* A, double* V) {
 // so its singular values / right vectors are those of the 2N x N matrix
 // [R*diag(d); diag(sq)].  The diagonal block is folded into the triangle by
 // Givens rotations (which also act on [qtf; 0]), then Jacobi runs on N x N.
-// Outputs: s, V, suf = s * (U^T f_aug), and Rh = R*diag(d) (packed) for the
-// quadratic-model evaluations (trf.py:69-74,100-102).
+// Outputs: s, Vt (row j = right singular vector j), suf = s * (U^T f_aug),
+// and Rh = R*diag(d) (packed) for the quadratic-model evaluations
+// (trf.py:69-74,100-102).
 template <int N>
 BLSQ_HD void hat_svd(const double* R, const double* qtf, const double* d,
-                     const double* diag_h, double* Rh, double* s, double* V,
+                     const double* diag_h, double* Rh, double* s, double* Vt,
                      double* suf) {
     double A[N * N];
     double b[N];
@@ -356,17 +374,17 @@ BLSQ_HD void hat_svd(const double* R, const double* qtf, const double* d,
             bz = fma(-sn, bi, c * bz);
         }
     }
-    jacobi_svd<N>(A, V);
+    jacobi_rows<N>(A, b);
     BLSQ_UNROLL
     for (int j = 0; j < N; j++) {
-        double nn = 0.0, ub = 0.0;
+        double nn = 0.0;
         BLSQ_UNROLL
-        for (int i = 0; i < N; i++) {
-            nn = fma(A[i * N + j], A[i * N + j], nn);
-            ub = fma(A[i * N + j], b[i], ub);
-        }
+        for (int i = 0; i < N; i++) nn = fma(A[j * N + i], A[j * N + i], nn);
         s[j] = sqrt(nn);
-        suf[j] = ub;            // = s_j * (u_j . b)
+        suf[j] = s[j] * b[j];
+        double inv = (s[j] > 0.0) ? 1.0 / s[j] : 0.0;
+        BLSQ_UNROLL
+        for (int i = 0; i < N; i++) Vt[j * N + i] = A[j * N + i] * inv;
     }
 }
 
@@ -613,8 +631,8 @@ BLSQ_HD bool trf_round(double* st, int* ist, const double* lin,
         return false;
     }
 
-    double Rh[S::NT], s[N], V[N * N], suf[N];
-    hat_svd<N>(st + S::R, st + S::QTF, d, diag_h, Rh, s, V, suf);
+    double Rh[S::NT], s[N], Vt[N * N], suf[N];
+    hat_svd<N>(st + S::R, st + S::QTF, d, diag_h, Rh, s, Vt, suf);
     double theta = 1.0 - g_norm;
     if (theta < 0.995) theta = 0.995;
 
@@ -622,7 +640,7 @@ BLSQ_HD bool trf_round(double* st, int* ist, const double* lin,
     double Delta = st[S::DELTA];
     double alpha = st[S::ALPHA];
     double p_h[N], p[N];
-    solve_lsq_trust_region<N>(P.m, suf, s, V, Delta, alpha, p_h);
+    solve_lsq_trust_region<N>(P.m, suf, s, Vt, Delta, alpha, p_h);
     st[S::ALPHA] = alpha;
     BLSQ_UNROLL
     for (int i = 0; i < N; i++) p[i] = d[i] * p_h[i];
@@ -968,38 +986,39 @@ BLSQ_HD bool dogbox_round(double* st, int* ist, const double* lin,
     // newton_step = lstsq(J_free, -f) (dogbox.py:197): minimum-norm solution
     // through the SVD of R[:, free], singular values <= eps*max(m,n_free)*smax
     // dropped (numpy.linalg.lstsq rcond=None).
-    double A[N * N], V[N * N];
+    double A[N * N], bq[N];
     BLSQ_UNROLL
     for (int i = 0; i < N; i++) {
+        bq[i] = st[S::QTF + i];
         BLSQ_UNROLL
         for (int j = 0; j < N; j++)
             A[i * N + j] = (j >= i && free_[j])
                                ? st[S::R + tri_index<N>(i, j)] : 0.0;
     }
-    jacobi_svd<N>(A, V);
-    double sv[N], ub_[N], smax = 0.0;
+    jacobi_rows<N>(A, bq);          // rows: s_j v_j^T ; bq: U^T (Q^T f)
+    double sv2[N], smax2 = 0.0;
     BLSQ_UNROLL
     for (int j = 0; j < N; j++) {
-        double nn = 0.0, ubj = 0.0;
+        double nn = 0.0;
         BLSQ_UNROLL
-        for (int i = 0; i < N; i++) {
-            nn = fma(A[i * N + j], A[i * N + j], nn);
-            ubj = fma(A[i * N + j], st[S::QTF + i], ubj);
-        }
-        sv[j] = sqrt(nn);
-        ub_[j] = ubj;                // s_j * (u_j . qtf)
-        if (sv[j] > smax) smax = sv[j];
+        for (int i = 0; i < N; i++) nn = fma(A[j * N + i], A[j * N + i], nn);
+        sv2[j] = nn;                 // s_j^2
+        if (nn > smax2) smax2 = nn;
     }
     int mx = P.m > nfree ? P.m : nfree;
-    double cut = EPS * mx * smax;
+    double cut = EPS * mx * sqrt(smax2);
     double w[N];
     BLSQ_UNROLL
     for (int j = 0; j < N; j++)
-        w[j] = (sv[j] > cut) ? (ub_[j] / sv[j]) / sv[j] : 0.0;
+        w[j] = (sqrt(sv2[j]) > cut) ? bq[j] / sv2[j] : 0.0;
     double newton[N], cauchy[N];
     BLSQ_UNROLL
-    for (int i = 0; i < N; i++)
-        newton[i] = free_[i] ? -dot<N>(V + i * N, w) : 0.0;
+    for (int i = 0; i < N; i++) {
+        double acc = 0.0;
+        BLSQ_UNROLL
+        for (int j = 0; j < N; j++) acc = fma(A[j * N + i], w[j], acc);
+        newton[i] = free_[i] ? -acc : 0.0;
+    }
     // cauchy = -(g.g)/(Jg.Jg) g  (dogbox.py:198-199), |J_free g| = |R g_free|
     double gf[N], Jg[N];
     BLSQ_UNROLL

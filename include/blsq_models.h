@@ -1,0 +1,32 @@
+/* blsq_models.h -- residual/Jacobian callbacks of the synthetic workloads
+ * named in BASELINE.json (configs C2, C3) as single fused CUDA kernels.
+ *
+ * These are USER-SIDE code: what a caller of least_squares would otherwise
+ * write as a chain of PyTorch elementwise ops (bounded_lsq_b200/synthetic.py
+ * fun_t / jac_t).  They are not part of the reference boundary in blsq.h; they
+ * exist so bench.py can show the solver with callbacks that do not dominate
+ * the run.  Same operation order as the torch forms, so results are bit
+ * identical to them.
+ *
+ * idx (nullable) maps row s of X/F/J to the problem whose data row y[idx[s]]
+ * it uses -- the active-set gather is fused into the load.
+ */
+#ifndef BLSQ_MODELS_H_
+#define BLSQ_MODELS_H_
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* y = a e^{-b t} + c e^{-d t}: F (A, m) = model - y[idx]; J (A, m, 4) or null */
+int blsq_model_expdecay2(int64_t A, const int64_t* idx, int m, const double* t,
+                         const double* X, const double* y, double* F, double* J,
+                         void* stream);
+/* y = A e^{-((t-mu)/sigma)^2/2} + c0 + c1 t + c2 t^2: F (A, m) */
+int blsq_model_gausspeak(int64_t A, const int64_t* idx, int m, const double* t,
+                         const double* X, const double* y, double* F,
+                         void* stream);
+#ifdef __cplusplus
+}
+#endif
+#endif

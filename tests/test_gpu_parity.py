@@ -105,3 +105,39 @@ def test_large_batch_properties(lib, dev):
     assert bool((xs == xs[0:1]).all())
     ns = res.nfev[:k].reshape(-1, 4096)
     assert bool((ns == ns[0:1]).all())
+
+
+def test_fused_model_callbacks_bit_identical(lib, dev):
+    """The fused CUDA callbacks (user-side op, include/blsq_models.h) compute
+    exactly what the torch elementwise chains compute, also through idx."""
+    from bounded_lsq_b200 import models, least_squares_batched, PerProblem
+    from bounded_lsq_b200.synthetic import ExpDecay2, GaussPeak
+    rng = np.random.default_rng(0)
+    for name, cls in (("ExpDecay2", ExpDecay2), ("GaussPeak", GaussPeak)):
+        model = cls()
+        B = 1000
+        _, y = model.make_data(B, seed=9)
+        y = cases.T(y, dev)
+        X = cases.T(rng.uniform(model.lb + 0.2, model.ub - 0.2, (B, model.n)), dev)
+        fun, jac = models.callbacks(name, "exact" if name == "ExpDecay2" else "2-point")
+        F = fun(X, None, y)
+        assert cases.bits(F.cpu().numpy(), model.fun_t(X, y).cpu().numpy())
+        idx = torch.arange(0, B, 3, device=dev)
+        Fi = fun(X[idx].contiguous(), idx, y)
+        assert cases.bits(Fi.cpu().numpy(), F[idx].cpu().numpy())
+        if name == "ExpDecay2":
+            J = jac(X, None, y)
+            assert cases.bits(J.cpu().numpy(), model.jac_t(X, y).cpu().numpy())
+    # and a whole solve gives identical answers with either kind of callback
+    model = ExpDecay2()
+    z = np.load(cases.os.path.join(cases.GOLDEN, "c2_trf_exact.npz"))
+    y = cases.T(z["y"], dev)
+    X0 = cases.T(np.tile(model.x0, (y.shape[0], 1)), dev)
+    fun, jac = models.callbacks("ExpDecay2", "exact")
+    r1 = least_squares_batched(fun, X0, jac=jac, bounds=(model.lb, model.ub),
+                               method="trf", args=(PerProblem(y),))
+    r2 = least_squares_batched(model.fun_t, X0, jac=model.jac_t,
+                               bounds=(model.lb, model.ub), method="trf",
+                               args=(PerProblem(y),))
+    assert cases.bits(r1.x.cpu().numpy(), r2.x.cpu().numpy())
+    assert cases.bits(r1.nfev.cpu().numpy(), r2.nfev.cpu().numpy())
