@@ -85,7 +85,8 @@ def _as_f64(t, like, what):
 
 def solve_batched(lib, method, fun, jac, X0, lb, ub, ftol, xtol, gtol,
                   max_nfev, scaling, diff_step=None, check_every=1,
-                  compact_below=0.75, trace=None, timers=None):
+                  compact_below=0.75, tail_below=8192, trace=None,
+                  timers=None):
     """Run ``method`` ('trf' | 'dogbox') on B problems.
 
     fun(X, idx) -> (A, m); jac is a callable jac(X, idx) -> (A, m, n) or the
@@ -219,13 +220,19 @@ def solve_batched(lib, method, fun, jac, X0, lb, ub, ftol, xtol, gtol,
         rounds += 1
         if trace is not None:
             trace(rounds, idx, Xnew[:A], state, istate)
-        if rounds % check_every == 0 or rounds >= max_nfev:
-            st = istate[:, 0] if idx is None else istate[idx, 0]
-            running = st == L.STATUS_RUNNING
-            nrun = int(running.sum().item())          # the one host sync
+        # host look at the status flags: every round while the rounds are
+        # bandwidth-sized, every 4th once they are launch-latency sized
+        every = check_every if A > tail_below else max(check_every, 4)
+        if rounds % every == 0 or rounds >= max_nfev:
+            lib.call("blsq_count_running", A, ip, istate.data_ptr(),
+                     count.data_ptr(), stream)
+            launches += 1
+            nrun = int(count.item())                  # the one host sync
             if nrun == 0:
                 break
             if nrun <= compact_below * A:
+                st = istate[:, 0] if idx is None else istate[idx, 0]
+                running = st == L.STATUS_RUNNING
                 sel = running.nonzero(as_tuple=False).squeeze(1)
                 idx = sel if idx is None else idx.index_select(0, sel)
                 idx32 = idx.to(torch.int32)

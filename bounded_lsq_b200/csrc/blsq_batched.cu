@@ -335,10 +335,15 @@ __global__ void on_bound_kernel(int64_t B, int n,
 }
 
 __global__ void count_running_kernel(int64_t B,
+                                     const int32_t* __restrict__ idx,
                                      const int32_t* __restrict__ istate,
                                      int32_t* __restrict__ count) {
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    bool run = t < B && istate[t * IS_SIZE + IS_STATUS] == ST_RUNNING;
+    bool run = false;
+    if (t < B) {
+        int64_t pid = idx ? idx[t] : t;
+        run = istate[pid * IS_SIZE + IS_STATUS] == ST_RUNNING;
+    }
     unsigned bal = __ballot_sync(0xffffffffu, run);
     if ((threadIdx.x & 31) == 0 && bal) atomicAdd(count, __popc(bal));
 }
@@ -513,14 +518,14 @@ int blsq_dogbox_on_bound(int64_t B, int n, const int32_t* istate,
     return 0;
 }
 
-int blsq_count_running(int64_t B, const int32_t* istate, int32_t* count,
-                       void* stream) {
+int blsq_count_running(int64_t B, const int32_t* idx, const int32_t* istate,
+                       int32_t* count, void* stream) {
     if (B < 0 || !istate || !count) return BLSQ_E_BADARG;
     cudaError_t e = cudaMemsetAsync(count, 0, sizeof(int32_t), (cudaStream_t)stream);
     if (e != cudaSuccess) return (int)e;
     if (B == 0) return 0;
     int64_t blocks = (B + 255) / 256;
-    count_running_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(B, istate, count);
+    count_running_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(B, idx, istate, count);
     BLSQ_LAUNCH_CHECK();
     return 0;
 }

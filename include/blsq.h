@@ -145,9 +145,10 @@ int blsq_round_batched(int method, int64_t A, const int32_t* idx, int m, int n,
 int blsq_dogbox_on_bound(int64_t B, int n, const int32_t* istate,
                          int64_t* mask, void* stream);
 
-/* count[0] = number of problems still running (device int32) */
-int blsq_count_running(int64_t B, const int32_t* istate, int32_t* count,
-                       void* stream);
+/* count[0] = number of slots 0..A-1 (problem idx[s], or s when idx is null)
+ * still running (device int32) */
+int blsq_count_running(int64_t A, const int32_t* idx, const int32_t* istate,
+                       int32_t* count, void* stream);
 
 #ifdef __cplusplus
 }

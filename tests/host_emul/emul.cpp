@@ -296,10 +296,11 @@ int blsq_dogbox_on_bound(int64_t B, int n, const int32_t* istate,
     return 0;
 }
 
-int blsq_count_running(int64_t B, const int32_t* istate, int32_t* count, void*) {
+int blsq_count_running(int64_t B, const int32_t* idx, const int32_t* istate,
+                       int32_t* count, void*) {
     int c = 0;
     for (int64_t b = 0; b < B; b++)
-        c += istate[b * IS_SIZE + IS_STATUS] == ST_RUNNING;
+        c += istate[(idx ? idx[b] : b) * IS_SIZE + IS_STATUS] == ST_RUNNING;
     *count = c;
     return 0;
 }
