@@ -96,9 +96,11 @@ def run_reference_arm(args, w):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    per_core = 48 if w["jac"] == "exact" else 24
-    for _ in range(args.warmup):
-        cpu_fits_per_second(w, 2, cores)
+    # a step is a bounded sample: ~6 s of CPU work per core, so that pool
+    # start-up (fork + imports) stays a small part of the timed region
+    per_core = 256 if w["jac"] == "exact" else 96
+    for _ in range(min(args.warmup, 1)):
+        cpu_fits_per_second(w, 4, cores)
     t0 = time.perf_counter()
     fits = 0
     nfev = 0.0
