@@ -39,10 +39,9 @@ SIGNATURES = {
     "blsq_count_running": [_l, _p, _p, _p, _p],
     "blsq_model_expdecay2": [_l, _p, _i, _p, _p, _p, _p, _p, _p],
     "blsq_model_gausspeak": [_l, _p, _i, _p, _p, _p, _p, _p],
-    "blsq_tall_workspace_size": [_l, _i],
-    "blsq_tsqr_local": [_l, _i, _p, _p, _p, _p, _p],
-    "blsq_tall_round": [_i, _i, _i, _l, _p, _p, _p, _p, _p, _d, _d, _d, _i,
-                        _i, _p, _p, _p, _p],
+    "blsq_tall_gram": [_i, _l, _i, _p, _p, _p, _p, _p, _p],
+    "blsq_tall_factor": [_i, _i, _i, _l, _p, _p, _p],
+    "blsq_tall_sumsq": [_l, _p, _p, _p, _p],
 }
 
 METHOD_TRF = 0
@@ -79,6 +78,12 @@ class Lib:
         self._dll = C.CDLL(path)
         self._dll.blsq_error_string.restype = C.c_char_p
         self._dll.blsq_error_string.argtypes = [_i]
+        for name in ("blsq_tall_gram_work_size", "blsq_tall_fac_size",
+                     "blsq_tall_state_size"):
+            if hasattr(self._dll, name):
+                f = getattr(self._dll, name)
+                f.argtypes = [_i]
+                f.restype = _l
         self._fn = {}
         for name, args in SIGNATURES.items():
             try:

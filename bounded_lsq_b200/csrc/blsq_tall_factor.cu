@@ -1,0 +1,180 @@
+// Tall mode, the n x n factor step of CholeskyQR2 (one CTA, latency bound).
+//
+//   pass 1:  G = sum over ranks of J^T J  ->  R1 = chol(G) (upper), R1^-1,
+//            g = J^T f (trf.py:244 / dogbox.py:170), f.f
+//   pass 2:  G2 = sum over ranks of Y^T Y, Y = J R1^-1  ->  R2 = chol(G2),
+//            R = R2 R1  (J = Q R),  Q^T f = R2^-T (Y^T f)
+//
+// The rank partials are summed in rank order, so every rank of a row-sharded
+// run computes bit-identical factors (no broadcast needed).
+//
+// `fac` layout: blsq_tall_common.cuh (FacLayout).  R1^-1 is emitted in the
+// DMMA fragment order the pass-2 Gram kernel consumes: for every upper 8x8
+// block (kb <= jb), two k-halves of 32 lanes, lane -> element
+// (8 kb + 4 half + lane%4, 8 jb + lane/4).
+// info = 0, or 1000*pass + k + 1 when the Cholesky pivot k was not positive
+// (J numerically rank deficient: CholeskyQR2 does not apply).
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/blsq.h"
+#include "blsq_tall_common.cuh"
+
+#define BLSQ_LAUNCH_CHECK()                                  \
+    do {                                                     \
+        cudaError_t e_ = cudaGetLastError();                 \
+        if (e_ != cudaSuccess) return (int)e_;               \
+    } while (0)
+
+namespace {
+
+constexpr int FAC_THREADS = 1024;
+constexpr int FAC_SMEM_MAX_N = 128;      // n x n doubles in shared memory up to here
+
+// in-place upper Cholesky of the upper triangle of M (n x n, row-major):
+// M = R^T R.  Returns 0 or k+1 for the first non-positive pivot.
+__device__ int chol_upper(double* M, int n) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int k = 0; k < n; k++) {
+        const double piv = M[k * n + k];
+        if (!(piv > 0.0)) return k + 1;            // uniform: everyone reads the same value
+        const double r = sqrt(piv);
+        __syncthreads();                            // all have read the pivot
+        for (int j = k + tid; j < n; j += nt) M[k * n + j] = (j == k) ? r : M[k * n + j] / r;
+        __syncthreads();
+        const int w = n - k - 1;
+        for (int e = tid; e < w * w; e += nt) {
+            const int i = k + 1 + e / w, j = k + 1 + e % w;
+            if (j >= i) M[i * n + j] = fma(-M[k * n + i], M[k * n + j], M[i * n + j]);
+        }
+        __syncthreads();
+    }
+    return 0;
+}
+
+// X = R^-1 for upper triangular R; one warp per column (back substitution,
+// lanes over the inner product).  Entries below the diagonal are zeroed.
+__device__ void inv_upper(const double* R, double* X, int n) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int j = warp; j < n; j += nw) {
+        for (int i = n - 1; i > j; i--)
+            if (lane == 0) X[i * n + j] = 0.0;
+        if (lane == 0) X[j * n + j] = 1.0 / R[j * n + j];
+        __syncwarp();
+        for (int i = j - 1; i >= 0; i--) {
+            double s = 0.0;
+            for (int k = i + 1 + lane; k <= j; k += 32) s = fma(R[i * n + k], X[k * n + j], s);
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+            if (lane == 0) X[i * n + j] = -s / R[i * n + i];
+            __syncwarp();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(FAC_THREADS, 1)
+tall_factor_kernel(int pass, int n, int nranks, int64_t gstride, const double* __restrict__ grams,
+                   double* __restrict__ fac, int use_smem) {
+    extern __shared__ __align__(16) double fsm[];
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int n2 = n * n;
+    const blsq_tall::FacLayout FL(n);
+    double* R1 = fac + FL.R1;
+    double* R = fac + FL.R;
+    double* scratch = fac + FL.SCR;
+    double* qtf = fac + FL.QTF;
+    double* g = fac + FL.G;
+    double* obj = fac + FL.OBJ;
+    double* info = fac + FL.INFO;
+    double* rinvp = fac + FL.RINVP;
+    double* M = use_smem ? fsm : scratch;
+
+    // fixed-order sum over the ranks
+    for (int e = tid; e < n2 + n + 1; e += nt) {
+        double s = 0.0;
+        for (int r = 0; r < nranks; r++) s += grams[(size_t)r * gstride + e];
+        if (e < n2) M[e] = s;
+        else if (pass == 1) {
+            if (e < n2 + n) g[e - n2] = s; else obj[0] = s;
+        } else if (e < n2 + n) {
+            qtf[e - n2] = s;                 // Y^T f for now
+        }
+    }
+    __syncthreads();
+    const int bad = chol_upper(M, n);
+    if (bad) {
+        if (tid == 0) info[0] = 1000.0 * pass + bad;
+        return;
+    }
+    if (pass == 1) {
+        for (int e = tid; e < n2; e += nt) {
+            const int i = e / n, j = e % n;
+            R1[e] = (j >= i) ? M[e] : 0.0;
+        }
+        __syncthreads();
+        // dense inverse into a free n x n region, then the fragment order
+        double* X = use_smem ? scratch : R;
+        inv_upper(M, X, n);
+        __syncthreads();
+        const int nb = FL.nb;
+        const int nblk = nb * (nb + 1) / 2;
+        for (int e = tid; e < nblk * 64; e += nt) {
+            const int q = e >> 6, half = (e >> 5) & 1, lane = e & 31;
+            int kb = 0, qq = q;
+            while (qq >= nb - kb) { qq -= nb - kb; kb++; }
+            const int jb = kb + qq;
+            const int r = 8 * kb + 4 * half + (lane & 3), c = 8 * jb + (lane >> 2);
+            rinvp[e] = (r < n && c < n && c >= r) ? X[r * n + c] : 0.0;
+        }
+        if (tid == 0) info[0] = 0.0;
+        return;
+    }
+    // pass 2: R = R2 R1 (upper x upper), Q^T f = R2^-T z
+    for (int e = tid; e < n2; e += nt) {
+        const int i = e / n, j = e % n;
+        double s = 0.0;
+        if (j >= i)
+            for (int k = i; k <= j; k++) s = fma(M[i * n + k], R1[k * n + j], s);
+        R[e] = s;
+    }
+    if (tid < 32) {
+        // forward substitution with R2^T, one warp
+        for (int i = 0; i < n; i++) {
+            double s = 0.0;
+            for (int k = tid; k < i; k += 32) s = fma(M[k * n + i], qtf[k], s);
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+            if (tid == 0) qtf[i] = (qtf[i] - s) / M[i * n + i];
+            __syncwarp();
+        }
+    }
+    if (tid == 0) info[0] = 0.0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int64_t blsq_tall_fac_size(int n) {
+    if (n < 2 || n > 256) return BLSQ_E_UNSUPPORTED;
+    return blsq_tall::FacLayout(n).SIZE;
+}
+
+int blsq_tall_factor(int pass, int n, int nranks, int64_t gstride, const double* grams,
+                     double* fac, void* stream) {
+    if ((pass != 1 && pass != 2) || nranks < 1 || !grams || !fac) return BLSQ_E_BADARG;
+    if (n < 2 || n > 256) return BLSQ_E_UNSUPPORTED;
+    if (gstride < (int64_t)n * n + n + 1) return BLSQ_E_BADARG;
+    const int use_smem = n <= FAC_SMEM_MAX_N;
+    const size_t smem = use_smem ? (size_t)n * n * 8 : 0;
+    cudaError_t e = cudaFuncSetAttribute(tall_factor_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         FAC_SMEM_MAX_N * FAC_SMEM_MAX_N * 8);
+    if (e != cudaSuccess) return (int)e;
+    tall_factor_kernel<<<1, FAC_THREADS, smem, (cudaStream_t)stream>>>(pass, n, nranks, gstride,
+                                                                        grams, fac, use_smem);
+    BLSQ_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // extern "C"

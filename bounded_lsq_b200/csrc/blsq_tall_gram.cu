@@ -1,0 +1,544 @@
+// Tall mode, the O(m n^2) part: Gram passes of CholeskyQR2 on [J | f] with
+// FP64 tensor-core tiles (DMMA, mma.sync.m8n8k4.f64) staged through TMA bulk
+// copies, plus the ||f||^2 reduction of a trial evaluation.
+//
+// Stands in for the dense factorisations of the reference on one tall problem:
+//   trf.py:244      g = J^T f
+//   trf.py:264-274  svd([J_h; diag]) -- via J = QR, see DESIGN.md section 2.2
+//   dogbox.py:170,197-199  J^T f, lstsq(J_free, -f), J_free g_free
+//
+// gram_kernel<NB, PASS>: persistent CTAs (one per SM).  One producer warp
+// streams 64-row tiles of J (row-major, n = up to 8*NB columns) and f into a
+// ring of shared-memory stages, one cp.async.bulk per row so that the rows can
+// be padded (LD = 8*NB + 4 doubles) and every fragment load below is bank
+// conflict free; mbarriers carry the full/empty hand-shake.  Consumer warps:
+//   PASS 2 only:  Y = tile * Rinv (Rinv = R1^-1 upper triangular) by DMMA into
+//                 a second shared buffer,
+//   both passes:  the upper 8x8 blocks of G += Y^T Y (or J^T J) by DMMA, the
+//                 blocks split over ROLES warp roles, the rows of the tile over
+//                 the KS warps of a role; role 0 also accumulates Y^T f, f.f.
+// Partials are written per CTA and summed in CTA order by gram_reduce_kernel,
+// so the result is deterministic for a given device.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <utility>
+
+#include "../../include/blsq.h"
+#include "blsq_tall_common.cuh"
+
+#define BLSQ_LAUNCH_CHECK()                                  \
+    do {                                                     \
+        cudaError_t e_ = cudaGetLastError();                 \
+        if (e_ != cudaSuccess) return (int)e_;               \
+    } while (0)
+
+namespace {
+
+// ---- PTX helpers ----------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// TMA bulk copy global -> shared, completion counted in bytes on `bar`
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes,
+                                         uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+            "r"(smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+// D(8x8) += A(8x4, row) * B(4x8, col); lane holds a = A[lane/4][lane%4],
+// b = B[lane%4][lane/4], c = C[lane/4][2*(lane%4) + {0,1}]
+__device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+        : "+d"(c[0]), "+d"(c[1])
+        : "d"(a), "d"(b));
+}
+
+// ---- block bookkeeping ------------------------------------------------------
+// upper-triangle blocks (i <= j < NB) enumerated row by row
+template <int NB>
+struct Tri {
+    static constexpr int COUNT = NB * (NB + 1) / 2;
+    __host__ __device__ static constexpr int row(int q) {
+        int i = 0;
+        while (q >= NB - i) { q -= NB - i; i++; }
+        return i;
+    }
+    __host__ __device__ static constexpr int col(int q) {
+        int i = 0;
+        while (q >= NB - i) { q -= NB - i; i++; }
+        return i + q;
+    }
+    __host__ __device__ static constexpr int index(int i, int j) {
+        return i * NB - (i * (i - 1)) / 2 + (j - i);
+    }
+};
+
+template <int NB> struct GramCfg;
+template <> struct GramCfg<2>  { static constexpr int T = 64, S = 4, CW = 4, ROLES = 1, CG = 2; static constexpr bool RINV_SMEM = true; };
+template <> struct GramCfg<4>  { static constexpr int T = 64, S = 4, CW = 8, ROLES = 1, CG = 4; static constexpr bool RINV_SMEM = true; };
+template <> struct GramCfg<8>  { static constexpr int T = 64, S = 4, CW = 8, ROLES = 2, CG = 8; static constexpr bool RINV_SMEM = true; };
+template <> struct GramCfg<16> { static constexpr int T = 64, S = 2, CW = 8, ROLES = 8, CG = 8; static constexpr bool RINV_SMEM = false; };
+template <> struct GramCfg<32> { static constexpr int T = 32, S = 2, CW = 8, ROLES = 8, CG = 8; static constexpr bool RINV_SMEM = false; };
+
+// Shared-memory layout of one tile of T rows.  The tile is kept as four
+// QUARTERS of QR = T/4 consecutive rows, each quarter dense (row stride RS = n)
+// so that ONE bulk copy moves it, and quarter h starts 4 doubles (8 banks)
+// after a multiple of 32 banks.  A DMMA k-chunk takes its four k rows from the
+// four quarters (row kc of each), which makes every fragment load conflict
+// free: lanes (lr, lc) read double lr of row kc in quarter lc.
+template <int NB, int PASS>
+struct GramLayout {
+    typedef GramCfg<NB> C;
+    static constexpr int W = 8 * NB;            // padded column count
+    static constexpr int QR = C::T / 4;         // rows per quarter
+    static constexpr int QS = QR * W + 4;       // quarter stride (doubles)
+    static constexpr int NBLK = Tri<NB>::COUNT;
+    static constexpr int BPR = (NBLK + C::ROLES - 1) / C::ROLES;   // blocks per role
+    static constexpr int KS = C::CW / C::ROLES;                    // row split
+    static constexpr int THREADS = (C::CW + 1) * 32;
+    static constexpr int STAGE_DOUBLES = 4 * QS + C::T;            // tile + f
+    static constexpr int YBUF_DOUBLES = (PASS == 2) ? 4 * QS : 0;
+    static constexpr int RINV_DOUBLES = (PASS == 2 && C::RINV_SMEM) ? NBLK * 64 : 0;
+    static constexpr int PER = NBLK * 64 + W + 2;                  // one warp copy (even: double2 stores)
+    static constexpr int RED_DOUBLES = (KS > 1) ? KS * PER : 0;
+    static constexpr int RING_DOUBLES = C::S * STAGE_DOUBLES;
+    // the cross-warp reduction reuses the ring once the pipeline has drained
+    static constexpr int BASE_DOUBLES = RING_DOUBLES > RED_DOUBLES ? RING_DOUBLES : RED_DOUBLES;
+    static constexpr int MAIN_DOUBLES = BASE_DOUBLES + YBUF_DOUBLES + RINV_DOUBLES;
+    static constexpr size_t SMEM_BYTES = (size_t)MAIN_DOUBLES * 8 + 2 * C::S * 8 + 16;
+    // per-CTA partial record: G (W x W, upper blocks), g (W), f.f
+    static constexpr int REC = W * W + W + 2;
+};
+
+template <int NB, int Q0, int... Qs>
+__device__ __forceinline__ void mma_role_blocks(double (&acc)[sizeof...(Qs)][2],
+                                                const double (&frag)[NB],
+                                                std::integer_sequence<int, Qs...>) {
+    (dmma(acc[Qs], frag[Tri<NB>::row(Q0 + Qs)], frag[Tri<NB>::col(Q0 + Qs)]), ...);
+}
+
+// EXACT: n == 8*NB (no column padding, row stride is a compile-time constant)
+template <int NB, int PASS, bool EXACT, int ROLE>
+__device__ __forceinline__ void consumer_loop(int64_t m, const double* __restrict__ rinvp_g,
+                                              int n, double* smem, uint64_t* full,
+                                              uint64_t* empty, double* __restrict__ rec) {
+    typedef GramCfg<NB> C;
+    typedef GramLayout<NB, PASS> L;
+    constexpr int T = C::T, S = C::S, CW = C::CW, W = L::W, QR = L::QR, QS = L::QS;
+    constexpr int Q0 = ROLE * L::BPR;
+    constexpr int NQ = (Q0 + L::BPR <= L::NBLK) ? L::BPR : (L::NBLK - Q0);
+    constexpr int KS = L::KS;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ks = warp / C::ROLES;
+    const int lr = lane >> 2, lc = lane & 3;
+    const int RS = EXACT ? W : n;               // row stride inside a quarter
+
+    double* ybuf = smem + L::BASE_DOUBLES;
+    const double* rinvp = C::RINV_SMEM ? (ybuf + L::YBUF_DOUBLES) : rinvp_g;
+
+    double acc[NQ][2];
+#pragma unroll
+    for (int q = 0; q < NQ; q++) { acc[q][0] = 0.0; acc[q][1] = 0.0; }
+    double gf[NB], ff = 0.0;
+#pragma unroll
+    for (int b = 0; b < NB; b++) gf[b] = 0.0;
+
+    const int64_t ntiles = (m + T - 1) / T;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        mbar_wait(&full[stage], phase);
+        const double* tj = smem + (size_t)stage * L::STAGE_DOUBLES;
+        const double* tf = tj + 4 * QS;
+        if (PASS == 2) {
+            // ---- phase A: Y = tile * Rinv; a strip is 8 rows (two from each
+            //      quarter), an item is a strip x CG column blocks ----
+            constexpr int NSTRIP = T / 8;
+            constexpr int NCG = NB / C::CG;
+            constexpr int ITEMS = NSTRIP * NCG;
+            // everyone must be done reading ybuf of the previous tile
+            named_bar_sync(1, CW * 32);
+            for (int it = warp; it < ITEMS; it += CW) {
+                const int strip = it % NSTRIP;
+                const int cg = (NCG == 1) ? 0 : it / NSTRIP;
+                double y[C::CG][2];
+#pragma unroll
+                for (int jj = 0; jj < C::CG; jj++) { y[jj][0] = 0.0; y[jj][1] = 0.0; }
+                const int qrow = 2 * strip + (lr >> 2);
+                const double* arow = tj + (lr & 3) * QS + qrow * RS + lc;
+                if (NCG == 1) {
+#pragma unroll
+                    for (int kc = 0; kc < 2 * NB; kc++) {
+                        const double a = (EXACT || kc * 4 + lc < n) ? arow[kc * 4] : 0.0;
+#pragma unroll
+                        for (int jj = 0; jj < C::CG; jj++) {
+                            if (kc <= 2 * jj + 1) {
+                                const int q = Tri<NB>::index(kc >> 1, jj);
+                                const double b = C::RINV_SMEM
+                                    ? rinvp[(q * 2 + (kc & 1)) * 32 + lane]
+                                    : __ldg(rinvp + (q * 2 + (kc & 1)) * 32 + lane);
+                                dmma(y[jj], a, b);
+                            }
+                        }
+                    }
+                } else {
+                    const int kmax = 2 * (cg * C::CG + C::CG);     // chunks of 4 columns
+                    for (int kc = 0; kc < kmax; kc++) {
+                        const double a = (EXACT || kc * 4 + lc < n) ? arow[kc * 4] : 0.0;
+                        const int kb = kc >> 1;
+                        const int qrow0 = kb * NB - (kb * (kb - 1)) / 2 - kb;   // + j
+#pragma unroll
+                        for (int jj = 0; jj < C::CG; jj++) {
+                            const int j = cg * C::CG + jj;
+                            if (kc <= 2 * j + 1) {
+                                const int q = qrow0 + j;
+                                const double b = C::RINV_SMEM
+                                    ? rinvp[(q * 2 + (kc & 1)) * 32 + lane]
+                                    : __ldg(rinvp + (q * 2 + (kc & 1)) * 32 + lane);
+                                dmma(y[jj], a, b);
+                            }
+                        }
+                    }
+                }
+                double* yrow = ybuf + (lr & 3) * QS + qrow * W + 2 * lc;
+#pragma unroll
+                for (int jj = 0; jj < C::CG; jj++) {
+                    const int j = cg * C::CG + jj;
+                    *reinterpret_cast<double2*>(yrow + 8 * j) = make_double2(y[jj][0], y[jj][1]);
+                }
+            }
+            named_bar_sync(1, CW * 32);
+        }
+        // ---- phase B: G += src^T src; chunk kc = row kc of the four quarters ----
+        const double* src = (PASS == 2) ? ybuf : tj;
+        const int SRS = (PASS == 2) ? W : RS;
+#pragma unroll 2
+        for (int kc = ks; kc < QR; kc += KS) {
+            const double* base = src + lc * QS + kc * SRS + lr;
+            double frag[NB];
+#pragma unroll
+            for (int b = 0; b < NB; b++)
+                frag[b] = (PASS == 2 || EXACT || 8 * b + lr < n) ? base[8 * b] : 0.0;
+            mma_role_blocks<NB, Q0>(acc, frag, std::make_integer_sequence<int, NQ>{});
+            if (ROLE == 0) {
+                const double fk = tf[lc * QR + kc];
+#pragma unroll
+                for (int b = 0; b < NB; b++) gf[b] = fma(frag[b], fk, gf[b]);
+                if (lr == 0) ff = fma(fk, fk, ff);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[stage]);
+        if (++stage == S) { stage = 0; phase ^= 1; }
+    }
+
+    // ---- fold the KS row-split copies and write this CTA's record ----
+    if (ROLE == 0) {
+#pragma unroll
+        for (int b = 0; b < NB; b++) {
+            gf[b] += __shfl_xor_sync(0xffffffffu, gf[b], 1);
+            gf[b] += __shfl_xor_sync(0xffffffffu, gf[b], 2);
+        }
+        ff += __shfl_xor_sync(0xffffffffu, ff, 1);
+        ff += __shfl_xor_sync(0xffffffffu, ff, 2);
+    }
+    if (KS == 1) {
+#pragma unroll
+        for (int q = 0; q < NQ; q++) {
+            const int bi = Tri<NB>::row(Q0 + q), bj = Tri<NB>::col(Q0 + q);
+            double* dst = rec + (size_t)(8 * bi + lr) * W + 8 * bj + 2 * lc;
+            *reinterpret_cast<double2*>(dst) = make_double2(acc[q][0], acc[q][1]);
+        }
+        if (ROLE == 0) {
+            if (lc == 0) {
+#pragma unroll
+                for (int b = 0; b < NB; b++) rec[W * W + 8 * b + lr] = gf[b];
+            }
+            if (lane == 0) rec[W * W + W] = ff;
+        }
+        return;
+    }
+    // KS > 1: through shared memory.  Every bulk copy has landed (each was
+    // waited for); wait until every consumer warp has left its last tile
+    // before the ring is reused.
+    named_bar_sync(2, CW * 32);
+    double* red = smem + (size_t)ks * L::PER;
+#pragma unroll
+    for (int q = 0; q < NQ; q++)
+        *reinterpret_cast<double2*>(red + (Q0 + q) * 64 + lane * 2) =
+            make_double2(acc[q][0], acc[q][1]);
+    if (ROLE == 0) {
+        if (lc == 0) {
+#pragma unroll
+            for (int b = 0; b < NB; b++) red[L::NBLK * 64 + 8 * b + lr] = gf[b];
+        }
+        if (lane == 0) red[L::NBLK * 64 + W] = ff;
+    }
+}
+
+template <int NB, int PASS, bool EXACT, int... ROLES_>
+__device__ __forceinline__ void consumer_dispatch(int role, int64_t m, const double* rinvp_g,
+                                                  int n, double* smem, uint64_t* full,
+                                                  uint64_t* empty, double* rec,
+                                                  std::integer_sequence<int, ROLES_...>) {
+    ((role == ROLES_
+          ? (consumer_loop<NB, PASS, EXACT, ROLES_>(m, rinvp_g, n, smem, full, empty, rec), 0)
+          : 0),
+     ...);
+}
+
+template <int NB, int PASS, bool EXACT>
+__global__ void __launch_bounds__(GramLayout<NB, PASS>::THREADS, 1)
+gram_kernel(int64_t m, int n, const double* __restrict__ J, const double* __restrict__ f,
+            const double* __restrict__ rinvp_g, double* __restrict__ partial) {
+    typedef GramCfg<NB> C;
+    typedef GramLayout<NB, PASS> L;
+    constexpr int T = C::T, S = C::S, CW = C::CW, W = L::W, QR = L::QR, QS = L::QS;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* smem = reinterpret_cast<double*>(smem_raw);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + L::MAIN_DOUBLES);
+    uint64_t* empty = full + S;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double* rec = partial + (size_t)blockIdx.x * L::REC;
+    const int RS = EXACT ? W : n;
+
+    for (int i = threadIdx.x; i < L::MAIN_DOUBLES; i += L::THREADS) smem[i] = 0.0;
+    for (int i = threadIdx.x; i < L::REC; i += L::THREADS) rec[i] = 0.0;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; s++) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], CW);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (PASS == 2 && C::RINV_SMEM) {
+        double* rinv_s = smem + L::BASE_DOUBLES + L::YBUF_DOUBLES;
+        for (int e = threadIdx.x; e < L::NBLK * 64; e += L::THREADS) rinv_s[e] = rinvp_g[e];
+    }
+    // make the generic-proxy zero fill visible before the async proxy writes
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+
+    const int64_t ntiles = (m + T - 1) / T;
+    if (warp == CW) {
+        // ---------------- producer ----------------
+        int stage = 0;
+        uint32_t phase = 0;
+        const uint32_t q_bytes = (uint32_t)(QR * n) * 8u;
+        for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            const int64_t row0 = t * T;
+            const int rows = (m - row0 < T) ? (int)(m - row0) : T;
+            double* dj = smem + (size_t)stage * L::STAGE_DOUBLES;
+            double* df = dj + 4 * QS;
+            if (rows == T) {
+                if (lane == 0) mbar_expect_tx(&full[stage], 4u * q_bytes + T * 8u);
+                __syncwarp();
+                if (lane < 4)
+                    bulk_g2s(dj + lane * QS, J + (row0 + lane * QR) * n, q_bytes, &full[stage]);
+                else if (lane == 4)
+                    bulk_g2s(df, f + row0, T * 8u, &full[stage]);
+            } else {
+                // ragged last tile: plain loads, rows past m are zero
+                for (int e = lane; e < T * n; e += 32) {
+                    const int r = e / n, c = e % n;
+                    dj[(r / QR) * QS + (r % QR) * RS + c] = (r < rows) ? J[(row0 + r) * n + c] : 0.0;
+                }
+                for (int r = lane; r < T; r += 32) df[r] = (r < rows) ? f[row0 + r] : 0.0;
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full[stage]);
+            }
+            if (++stage == S) { stage = 0; phase ^= 1; }
+        }
+    } else {
+        consumer_dispatch<NB, PASS, EXACT>(warp % C::ROLES, m, rinvp_g, n, smem, full, empty, rec,
+                                           std::make_integer_sequence<int, C::ROLES>{});
+    }
+    if (L::KS > 1) {
+        // fixed-order sum over the row-split copies
+        __syncthreads();
+        constexpr int PER = L::PER;
+        for (int e = threadIdx.x; e < PER - 1; e += L::THREADS) {
+            double s = 0.0;
+#pragma unroll
+            for (int k = 0; k < L::KS; k++) s += smem[(size_t)k * PER + e];
+            if (e < L::NBLK * 64) {
+                const int q = e >> 6, ln = (e >> 1) & 31, c = e & 1;
+                int bi = 0, qq = q;
+                while (qq >= NB - bi) { qq -= NB - bi; bi++; }
+                const int bj = bi + qq;
+                rec[(size_t)(8 * bi + (ln >> 2)) * W + 8 * bj + 2 * (ln & 3) + c] = s;
+            } else {
+                rec[W * W + (e - L::NBLK * 64)] = s;
+            }
+        }
+    }
+}
+
+// out (n*n + n + 1 doubles): G (n x n row-major, upper triangle valid), g, f.f
+// = sum over the P per-CTA records, in CTA order.
+__global__ void gram_reduce_kernel(int P, int W, int REC, int n,
+                                   const double* __restrict__ partial,
+                                   double* __restrict__ out) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    const int total = n * n + n + 1;
+    if (e >= total) return;
+    int src;
+    if (e < n * n) {
+        const int r = e / n, c = e % n;
+        if (c < r) { out[e] = 0.0; return; }
+        src = r * W + c;
+    } else if (e < n * n + n) {
+        src = W * W + (e - n * n);
+    } else {
+        src = W * W + W;
+    }
+    double s = 0.0;
+    for (int p = 0; p < P; p++) s += partial[(size_t)p * REC + src];
+    out[e] = s;
+}
+
+// ---- ||f||^2 of a trial evaluation (trf.py:311, dogbox.py:224) -------------
+__global__ void __launch_bounds__(256) sumsq_partial_kernel(int64_t m, const double* __restrict__ f,
+                                                            double* __restrict__ part) {
+    __shared__ double sh[8];
+    double s = 0.0;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += stride) {
+        const double v = f[i];
+        s = fma(v, v, s);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; w++) t += sh[w];
+        part[blockIdx.x] = t;
+    }
+}
+__global__ void sumsq_final_kernel(int P, const double* __restrict__ part,
+                                   double* __restrict__ out) {
+    // one warp, fixed order
+    double s = 0.0;
+    for (int p = threadIdx.x; p < P; p += 32) s += part[p];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if (threadIdx.x == 0) out[0] = s;
+}
+
+int sm_count() {
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 148;
+    return sms > 0 ? sms : 148;
+}
+
+using blsq_tall::nb_for;
+
+template <int NB, int PASS, bool EXACT>
+int launch_gram_e(int64_t m, int n, const double* J, const double* f, const double* rinvp,
+                  double* work, double* out, cudaStream_t s) {
+    typedef GramLayout<NB, PASS> L;
+    typedef GramCfg<NB> C;
+    const int sms = sm_count();
+    const int64_t ntiles = (m + C::T - 1) / C::T;
+    int grid = (int)(ntiles < sms ? (ntiles > 0 ? ntiles : 1) : sms);
+    cudaError_t e = cudaFuncSetAttribute(gram_kernel<NB, PASS, EXACT>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)L::SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    gram_kernel<NB, PASS, EXACT><<<grid, L::THREADS, L::SMEM_BYTES, s>>>(m, n, J, f, rinvp, work);
+    BLSQ_LAUNCH_CHECK();
+    const int total = n * n + n + 1;
+    gram_reduce_kernel<<<(total + 255) / 256, 256, 0, s>>>(grid, L::W, L::REC, n, work, out);
+    BLSQ_LAUNCH_CHECK();
+    return 0;
+}
+
+template <int NB, int PASS>
+int launch_gram(int64_t m, int n, const double* J, const double* f, const double* rinvp,
+                double* work, double* out, cudaStream_t s) {
+    if (n == 8 * NB) return launch_gram_e<NB, PASS, true>(m, n, J, f, rinvp, work, out, s);
+    return launch_gram_e<NB, PASS, false>(m, n, J, f, rinvp, work, out, s);
+}
+
+}  // namespace
+
+extern "C" {
+
+int64_t blsq_tall_gram_work_size(int n) {
+    if (n < 2 || n > 256) return BLSQ_E_UNSUPPORTED;
+    const int W = 8 * nb_for(n);
+    return (int64_t)sm_count() * (W * W + W + 2);
+}
+
+int blsq_tall_gram(int pass, int64_t m, int n, const double* J, const double* f,
+                   const double* Rinv, double* work, double* out, void* stream) {
+    if (m < 0 || !J || !f || !work || !out) return BLSQ_E_BADARG;
+    if (pass != 1 && pass != 2) return BLSQ_E_BADARG;
+    if (pass == 2 && !Rinv) return BLSQ_E_BADARG;
+    // rows are moved by 16-byte-granular bulk copies
+    if (n < 2 || n > 256 || (n & 1)) return BLSQ_E_UNSUPPORTED;
+    if (((uintptr_t)J & 15) || ((uintptr_t)f & 15)) return BLSQ_E_BADARG;
+    cudaStream_t s = (cudaStream_t)stream;
+#define BLSQ_GRAM_CASE(NB_)                                                         \
+    case NB_:                                                                       \
+        return pass == 1 ? launch_gram<NB_, 1>(m, n, J, f, Rinv, work, out, s)      \
+                         : launch_gram<NB_, 2>(m, n, J, f, Rinv, work, out, s);
+    switch (nb_for(n)) {
+        BLSQ_GRAM_CASE(2)
+        BLSQ_GRAM_CASE(4)
+        BLSQ_GRAM_CASE(8)
+        BLSQ_GRAM_CASE(16)
+        BLSQ_GRAM_CASE(32)
+    }
+#undef BLSQ_GRAM_CASE
+    return BLSQ_E_UNSUPPORTED;
+}
+
+int blsq_tall_sumsq(int64_t m, const double* f, double* work, double* out, void* stream) {
+    if (m < 0 || !f || !work || !out) return BLSQ_E_BADARG;
+    const int sms = sm_count();
+    int64_t want = (m + 256 * 8 - 1) / (256 * 8);
+    int grid = (int)(want < 1 ? 1 : (want > 4 * sms ? 4 * sms : want));
+    sumsq_partial_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(m, f, work);
+    BLSQ_LAUNCH_CHECK();
+    sumsq_final_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(grid, work, out);
+    BLSQ_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // extern "C"

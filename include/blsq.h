@@ -150,6 +150,33 @@ int blsq_dogbox_on_bound(int64_t B, int n, const int32_t* istate,
 int blsq_count_running(int64_t A, const int32_t* idx, const int32_t* istate,
                        int32_t* count, void* stream);
 
+
+/* ---- tall mode: one problem, m_local rows on this rank, n even, n <= 256 --
+ *
+ * Per Jacobian evaluation (trf.py:244,264-274; dogbox.py:170,197-199) the
+ * rank runs CholeskyQR2 on [J | f]:
+ *   blsq_tall_gram(1)   -> record {J^T J, J^T f, f.f} of this rank's rows
+ *   (all-gather the records over the ranks)
+ *   blsq_tall_factor(1) -> R1 = chol(sum of records), R1^-1, g, f.f
+ *   blsq_tall_gram(2)   -> record {Y^T Y, Y^T f}, Y = J R1^-1
+ *   (all-gather)
+ *   blsq_tall_factor(2) -> R = chol(.) R1 (J = Q R), Q^T f
+ * A record is n*n + n + 1 doubles: G row-major (upper triangle valid), then
+ * the n-vector, then f.f.  `fac` holds blsq_tall_fac_size(n) doubles:
+ * R1 | R1^-1 | R | scratch (n*n each) | Q^T f (n) | g (n) | f.f | info.
+ * info != 0: the Gram matrix was not numerically positive definite. */
+#define BLSQ_MAX_TALL_N 256
+int64_t blsq_tall_gram_work_size(int n);   /* doubles of `work` for blsq_tall_gram */
+int64_t blsq_tall_fac_size(int n);
+int blsq_tall_gram(int pass, int64_t m, int n, const double* J, const double* f,
+                   const double* Rinv, double* work, double* out, void* stream);
+int blsq_tall_factor(int pass, int n, int nranks, int64_t gstride,
+                     const double* grams, double* fac, void* stream);
+/* out[0] = sum f_i^2 over this rank's rows (trf.py:311, dogbox.py:224);
+ * work: 4 * (number of SMs) doubles */
+int blsq_tall_sumsq(int64_t m, const double* f, double* work, double* out,
+                    void* stream);
+
 #ifdef __cplusplus
 }
 #endif
