@@ -42,6 +42,9 @@ SIGNATURES = {
     "blsq_tall_gram": [_i, _l, _i, _p, _p, _p, _p, _p, _p],
     "blsq_tall_factor": [_i, _i, _i, _l, _p, _p, _p],
     "blsq_tall_sumsq": [_l, _p, _p, _p, _p],
+    "blsq_tall_layout": [_i, _p],
+    "blsq_tall_round": [_i, _i, _i, _l, _i, _p, _p, _p, _p, _p, _p, _d, _d, _d,
+                        _i, _i, _i, _p, _p, _p, _p],
 }
 
 METHOD_TRF = 0
@@ -132,6 +135,18 @@ class Lib:
         keys = ("size", "x", "x_new", "scale", "obj", "delta", "gnorm", "g",
                 "alpha")
         return dict(zip(keys, list(out)))
+
+    def tall_layout(self, n):
+        out = (C.c_int64 * 16)()
+        rc = self._fn["blsq_tall_layout"](n, C.cast(out, _p))
+        if rc != 0:
+            raise BlsqError(f"blsq_tall_layout({n}) failed: {rc}")
+        keys = ("state_size", "istate_size", "x", "x_new", "obj", "delta",
+                "gnorm", "on_bound", "fac_size", "R", "qtf", "g", "fobj",
+                "info", "rinvp", "scale")
+        d = dict(zip(keys, list(out)))
+        d["gram_work"] = int(self._dll.blsq_tall_gram_work_size(n))
+        return d
 
     def lin_record_size(self, n):
         rc = self._fn["blsq_lin_record_size"](n)

@@ -4,10 +4,16 @@
 #pragma once
 #include <stdint.h>
 
+#if defined(__CUDACC__)
+#define BLSQ_TALL_HD __host__ __device__
+#else
+#define BLSQ_TALL_HD
+#endif
+
 namespace blsq_tall {
 
 // number of 8-column blocks the Gram kernels are instantiated for
-inline __host__ __device__ int nb_for(int n) {
+inline BLSQ_TALL_HD int nb_for(int n) {
     if (n <= 16) return 2;
     if (n <= 32) return 4;
     if (n <= 64) return 8;
@@ -16,11 +22,12 @@ inline __host__ __device__ int nb_for(int n) {
 }
 
 // fac (doubles):  R1 | R | scratch (n*n each) | Q^T f (n) | g (n) | f.f | info |
+//                 shift1, shift2 |
 //                 R1^-1 in DMMA-fragment order (64 doubles per upper 8x8 block)
 struct FacLayout {
     int n, nb;
-    int64_t n2, R1, R, SCR, QTF, G, OBJ, INFO, RINVP, SIZE;
-    __host__ __device__ explicit FacLayout(int n_) : n(n_), nb(nb_for(n_)) {
+    int64_t n2, R1, R, SCR, QTF, G, OBJ, INFO, SHIFT, RINVP, SIZE;
+    BLSQ_TALL_HD explicit FacLayout(int n_) : n(n_), nb(nb_for(n_)) {
         n2 = (int64_t)n * n;
         R1 = 0;
         R = n2;
@@ -29,13 +36,14 @@ struct FacLayout {
         G = QTF + n;
         OBJ = G + n;
         INFO = OBJ + 1;
-        RINVP = (INFO + 1 + 1) & ~(int64_t)1;
+        SHIFT = INFO + 1;                 // diagonal shifts used by pass 1, 2
+        RINVP = (SHIFT + 2 + 1) & ~(int64_t)1;
         SIZE = RINVP + (int64_t)nb * (nb + 1) / 2 * 64;
     }
 };
 
 // index of block (i, j), i <= j < NB, in the row-by-row upper-triangle order
-inline __host__ __device__ int tri_block(int nb, int i, int j) {
+inline BLSQ_TALL_HD int tri_block(int nb, int i, int j) {
     return i * nb - (i * (i - 1)) / 2 + (j - i);
 }
 

@@ -32,12 +32,15 @@ constexpr int FAC_THREADS = 1024;
 constexpr int FAC_SMEM_MAX_N = 128;      // n x n doubles in shared memory up to here
 
 // in-place upper Cholesky of the upper triangle of M (n x n, row-major):
-// M = R^T R.  Returns 0 or k+1 for the first non-positive pivot.
-__device__ int chol_upper(double* M, int n) {
+// M = R^T R.  diag0[k] = the diagonal of the matrix before any shift.  A pivot
+// that has collapsed to rounding level (<= 8 n eps diag0[k]) stops the sweep:
+// returns k + 1 (0 = success) and the caller retries with a diagonal shift.
+__device__ int chol_upper(double* M, const double* diag0, int n) {
     const int tid = threadIdx.x, nt = blockDim.x;
+    const double tol = 8.0 * n * 2.220446049250313e-16;
     for (int k = 0; k < n; k++) {
         const double piv = M[k * n + k];
-        if (!(piv > 0.0)) return k + 1;            // uniform: everyone reads the same value
+        if (!(piv > tol * diag0[k])) return k + 1;   // uniform: everyone reads the same value
         const double r = sqrt(piv);
         __syncthreads();                            // all have read the pivot
         for (int j = k + tid; j < n; j += nt) M[k * n + j] = (j == k) ? r : M[k * n + j] / r;
@@ -87,21 +90,50 @@ tall_factor_kernel(int pass, int n, int nranks, int64_t gstride, const double* _
     double* obj = fac + FL.OBJ;
     double* info = fac + FL.INFO;
     double* rinvp = fac + FL.RINVP;
+    double* shifts = fac + FL.SHIFT;
     double* M = use_smem ? fsm : scratch;
 
-    // fixed-order sum over the ranks
-    for (int e = tid; e < n2 + n + 1; e += nt) {
-        double s = 0.0;
-        for (int r = 0; r < nranks; r++) s += grams[(size_t)r * gstride + e];
-        if (e < n2) M[e] = s;
-        else if (pass == 1) {
-            if (e < n2 + n) g[e - n2] = s; else obj[0] = s;
-        } else if (e < n2 + n) {
-            qtf[e - n2] = s;                 // Y^T f for now
+    // Cholesky of the rank-order sum of the records.  A rank-deficient (or
+    // worse than ~1e7 conditioned) Jacobian makes a pivot collapse; the sweep
+    // is then redone on G + shift*I, shift = 16 n eps max(diag G) (x10 per
+    // retry).  With both passes shifted R^T R = J^T J (1 + O(shift2)) +
+    // O(shift1 shift2) I, i.e. the null directions of J come out with a
+    // singular value of ~1e-13 |J| instead of 0 and everything else is
+    // unchanged to ~1e-14 (shifted CholeskyQR, Fukaya et al. 2020).
+    __shared__ double diag0[256];
+    __shared__ double dmax_s;
+    double shift = 0.0;
+    int bad = 0;
+    for (int attempt = 0; attempt < 12; attempt++) {
+        for (int e = tid; e < n2 + n + 1; e += nt) {
+            double s = 0.0;
+            for (int r = 0; r < nranks; r++) s += grams[(size_t)r * gstride + e];
+            if (e < n2) {
+                const int i = e / n, j = e % n;
+                if (i == j) { if (attempt == 0) diag0[i] = s; s += shift; }
+                M[e] = s;
+            } else if (attempt == 0) {
+                if (pass == 1) {
+                    if (e < n2 + n) g[e - n2] = s; else obj[0] = s;
+                } else if (e < n2 + n) {
+                    qtf[e - n2] = s;                 // Y^T f for now
+                }
+            }
         }
+        __syncthreads();
+        if (attempt == 0 && tid == 0) {
+            double d = 0.0;
+            for (int i = 0; i < n; i++) d = diag0[i] > d ? diag0[i] : d;
+            dmax_s = d;
+        }
+        __syncthreads();
+        bad = chol_upper(M, diag0, n);
+        if (!bad) break;
+        if (!(dmax_s > 0.0) || dmax_s != dmax_s) break;      // zero or NaN Jacobian
+        shift = (shift == 0.0) ? 16.0 * n * 2.220446049250313e-16 * dmax_s : shift * 10.0;
+        __syncthreads();
     }
-    __syncthreads();
-    const int bad = chol_upper(M, n);
+    if (tid == 0) shifts[pass - 1] = shift;
     if (bad) {
         if (tid == 0) info[0] = 1000.0 * pass + bad;
         return;

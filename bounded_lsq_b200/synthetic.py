@@ -134,7 +134,13 @@ class TallLinExp:
     single-process run over the concatenated shards see identical data.
     """
 
-    def __init__(self, m, n=64, seed=0, noise=0.01, dtype=np.float64):
+    def __init__(self, m, n=64, seed=0, noise=0.01, dtype=np.float64,
+                 x0_tail=(0.5, 1.0, 0.5, 1.0)):
+        # the default start (SURVEY 8d, config C4) has the two exponentials
+        # identical: J(x0) is exactly rank deficient and the symmetry is only
+        # broken by rounding, so TRF iterates are ulp-chaotic from the ~5th
+        # step on (the reference does not reproduce itself under 1-ulp noise
+        # either); parity tests that gate x and nfev use an asymmetric tail
         assert n >= 5
         self.m, self.n, self.k = m, n, n - 4
         rng = np.random.default_rng(seed)
@@ -143,7 +149,7 @@ class TallLinExp:
         self.x_true = np.concatenate([rng.uniform(-1.0, 1.0, self.k),
                                       [1.0, 2.0, 0.5, 3.0]])
         self.y = self._model(self.x_true) + noise * rng.standard_normal(m)
-        self.x0 = np.concatenate([np.full(self.k, 0.1), [0.5, 1.0, 0.5, 1.0]])
+        self.x0 = np.concatenate([np.full(self.k, 0.1), list(x0_tail)])
         self.lb = np.full(n, -0.5)
         self.ub = np.full(n, 5.0)
 

@@ -177,6 +177,32 @@ int blsq_tall_factor(int pass, int n, int nranks, int64_t gstride,
 int blsq_tall_sumsq(int64_t m, const double* f, double* work, double* out,
                     void* stream);
 
+
+/* The n x n tail of one round for the tall problem (one CTA).  `state`
+ * (blsq_tall_layout out[0] doubles) and `istate` (out[1] int32) persist
+ * between the calls; x, bounds and every n-sized quantity are replicated on
+ * all ranks and every rank runs the same calls on the same inputs.
+ *   phase 0  init: trf.py:201 / dogbox.py:131 -> state.x_new = start point
+ *   phase 1  judge: ||f(x_new)||^2 = sum of ssq_parts[0..nranks) (rank order);
+ *            ratio test, Delta/alpha update, termination tests, accept
+ *            (trf.py:310-352, dogbox.py:222-267).  istate[3] = accepted.
+ *   phase 2  propose: `fac` is the factor record of the Jacobian at state.x;
+ *            new_lin != 0 when it changed since the last call.  Coleman-Li
+ *            scaling, SVD of the hat-space triangle, LM parameter, candidates
+ *            (trf.py:238-308) or active set, Gauss-Newton/Cauchy, box dogleg
+ *            (dogbox.py:164-220) -> state.x_new, or a final istate[0] status.
+ * work: n*n doubles (used when n > 128).  scaling: n doubles or null ('jac').
+ * blsq_tall_layout: out[0..15] = state size, istate size, offsets of x,
+ * x_new, obj, Delta, optimality, on_bound (istate), fac size, offsets of R,
+ * Q^T f, g, f.f, info, packed R1^-1 inside fac, offset of scale. */
+int blsq_tall_layout(int n, int64_t* out_host);
+int blsq_tall_round(int method, int phase, int n, int64_t m_total, int nranks,
+                    const double* ssq_parts, const double* fac,
+                    const double* x0, const double* lb, const double* ub,
+                    const double* scaling, double ftol, double xtol,
+                    double gtol, int max_nfev, int first, int new_lin,
+                    double* state, int32_t* istate, double* work, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -408,12 +408,20 @@ def gen_batched(name, wl, method, fd, B, seed):
           f"{np.bincount(status).tolist()} oracle bitwise on {nbit}/{B}")
 
 
+ASYM_TAIL = (0.8, 1.5, 0.3, 4.0)
+
+
 def gen_tall():
     """C4-like tall problems at sizes the CPU reference finishes quickly."""
     out = {}
     metas = []
-    for tag, m, n, seed in (("a", 4096, 16, 3), ("b", 20000, 64, 0)):
-        wl = TallLinExp(m, n, seed=seed)
+    # a, b: the C4 start (symmetric exponentials, ulp-chaotic for TRF);
+    # c, d: asymmetric start, well conditioned along the whole path
+    for tag, m, n, seed, tail in (("a", 4096, 16, 3, None), ("b", 20000, 64, 0, None),
+                                  ("c", 4096, 16, 3, ASYM_TAIL),
+                                  ("d", 20000, 64, 0, ASYM_TAIL)):
+        wl = TallLinExp(m, n, seed=seed) if tail is None else \
+            TallLinExp(m, n, seed=seed, x0_tail=tail)
         for method in ("trf", "dogbox"):
             r, t = ref_solve(method, wl.fun_np, wl.jac_np, wl.x0, wl.lb, wl.ub)
             o, ot = orc_solve(method, wl.fun_np, wl.jac_np, wl.x0, wl.lb,
@@ -427,6 +435,7 @@ def gen_tall():
                 [rec["obj"], rec["status"], rec["nfev"], rec["njev"],
                  rec["optimality"], rec["ntrials"]])
             metas.append(dict(tag=tag, m=m, n=n, seed=seed, method=method,
+                              x0_tail=None if tail is None else list(tail),
                               bitwise=bit, status=rec["status"],
                               nfev=rec["nfev"], njev=rec["njev"],
                               nactive=int(np.count_nonzero(rec["mask"]))))
@@ -438,6 +447,9 @@ def gen_tall():
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "tall":
+        gen_tall()
+        sys.exit(0)
     rng = np.random.default_rng(20261018)
     gen_helpers(rng)
     gen_tr_subproblem(rng)

@@ -306,3 +306,203 @@ int blsq_count_running(int64_t B, const int32_t* idx, const int32_t* istate,
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------
+// Tall mode on the host (TEST ONLY): the same C ABI, CholeskyQR2 in plain loops
+// and blsq_tall_core.cuh run by a single "thread".
+// ---------------------------------------------------------------------------
+#include "../../bounded_lsq_b200/csrc/blsq_tall_core.cuh"
+
+namespace {
+using namespace blsq_tall;
+
+int host_chol_upper(double* M, const double* diag0, int n) {
+    const double tol = 8.0 * n * 2.220446049250313e-16;
+    for (int k = 0; k < n; k++) {
+        double piv = M[k * n + k];
+        if (!(piv > tol * diag0[k])) return k + 1;
+        double r = sqrt(piv);
+        for (int j = k; j < n; j++) M[k * n + j] = (j == k) ? r : M[k * n + j] / r;
+        for (int i = k + 1; i < n; i++)
+            for (int j = i; j < n; j++)
+                M[i * n + j] = fma(-M[k * n + i], M[k * n + j], M[i * n + j]);
+    }
+    return 0;
+}
+
+void host_inv_upper(const double* R, double* X, int n) {
+    for (int j = 0; j < n; j++) {
+        for (int i = j + 1; i < n; i++) X[i * n + j] = 0.0;
+        X[j * n + j] = 1.0 / R[j * n + j];
+        for (int i = j - 1; i >= 0; i--) {
+            double s = 0.0;
+            for (int k = i + 1; k <= j; k++) s = fma(R[i * n + k], X[k * n + j], s);
+            X[i * n + j] = -s / R[i * n + i];
+        }
+    }
+}
+}  // namespace
+
+extern "C" {
+
+int64_t blsq_tall_gram_work_size(int n) { return (n < 2 || n > 256) ? -2 : 8; }
+int64_t blsq_tall_fac_size(int n) { return (n < 2 || n > 256) ? -2 : FacLayout(n).SIZE; }
+
+int blsq_tall_gram(int pass, int64_t m, int n, const double* J, const double* f,
+                   const double* rinvp, double*, double* out, void*) {
+    if (n < 2 || n > 256 || (n & 1)) return BLSQ_E_UNSUPPORTED;
+    std::vector<double> X;
+    if (pass == 2) {
+        // unpack the fragment-ordered R1^-1
+        X.assign((size_t)n * n, 0.0);
+        const int nb = nb_for(n);
+        for (int kb = 0; kb < nb; kb++)
+            for (int jb = kb; jb < nb; jb++) {
+                const int q = tri_block(nb, kb, jb);
+                for (int half = 0; half < 2; half++)
+                    for (int lane = 0; lane < 32; lane++) {
+                        int r = 8 * kb + 4 * half + (lane & 3), c = 8 * jb + (lane >> 2);
+                        if (r < n && c < n) X[(size_t)r * n + c] = rinvp[(q * 2 + half) * 32 + lane];
+                    }
+            }
+    }
+    for (int e = 0; e < n * n + n + 1; e++) out[e] = 0.0;
+    std::vector<double> y(n);
+    for (int64_t r = 0; r < m; r++) {
+        const double* row = J + r * n;
+        if (pass == 2) {
+            for (int c = 0; c < n; c++) {
+                double s = 0.0;
+                for (int k = 0; k <= c; k++) s = fma(row[k], X[(size_t)k * n + c], s);
+                y[c] = s;
+            }
+        } else {
+            for (int c = 0; c < n; c++) y[c] = row[c];
+        }
+        for (int i = 0; i < n; i++) {
+            for (int j = i; j < n; j++) out[i * n + j] = fma(y[i], y[j], out[i * n + j]);
+            out[n * n + i] = fma(y[i], f[r], out[n * n + i]);
+        }
+        out[n * n + n] = fma(f[r], f[r], out[n * n + n]);
+    }
+    return 0;
+}
+
+int blsq_tall_factor(int pass, int n, int nranks, int64_t gstride, const double* grams,
+                     double* fac, void*) {
+    const FacLayout FL(n);
+    const int n2 = n * n;
+    std::vector<double> M(n2), diag0(n);
+    double shift = 0.0, dmax = 0.0;
+    int bad = 0;
+    for (int attempt = 0; attempt < 12; attempt++) {
+        for (int e = 0; e < n2 + n + 1; e++) {
+            double s = 0.0;
+            for (int r = 0; r < nranks; r++) s += grams[(size_t)r * gstride + e];
+            if (e < n2) {
+                if (e / n == e % n) { if (attempt == 0) diag0[e / n] = s; s += shift; }
+                M[e] = s;
+            } else if (attempt == 0) {
+                if (pass == 1) { if (e < n2 + n) fac[FL.G + e - n2] = s; else fac[FL.OBJ] = s; }
+                else if (e < n2 + n) fac[FL.QTF + e - n2] = s;
+            }
+        }
+        if (attempt == 0) for (int i = 0; i < n; i++) dmax = diag0[i] > dmax ? diag0[i] : dmax;
+        bad = host_chol_upper(M.data(), diag0.data(), n);
+        if (!bad) break;
+        if (!(dmax > 0.0)) break;
+        shift = (shift == 0.0) ? 16.0 * n * 2.220446049250313e-16 * dmax : shift * 10.0;
+    }
+    fac[FL.SHIFT + pass - 1] = shift;
+    if (bad) { fac[FL.INFO] = 1000.0 * pass + bad; return 0; }
+    if (pass == 1) {
+        for (int e = 0; e < n2; e++) fac[FL.R1 + e] = (e % n >= e / n) ? M[e] : 0.0;
+        std::vector<double> X(n2, 0.0);
+        host_inv_upper(M.data(), X.data(), n);
+        const int nb = FL.nb;
+        for (int kb = 0; kb < nb; kb++)
+            for (int jb = kb; jb < nb; jb++) {
+                const int q = tri_block(nb, kb, jb);
+                for (int half = 0; half < 2; half++)
+                    for (int lane = 0; lane < 32; lane++) {
+                        int r = 8 * kb + 4 * half + (lane & 3), c = 8 * jb + (lane >> 2);
+                        fac[FL.RINVP + (q * 2 + half) * 32 + lane] =
+                            (r < n && c < n && c >= r) ? X[(size_t)r * n + c] : 0.0;
+                    }
+            }
+        fac[FL.INFO] = 0.0;
+        return 0;
+    }
+    const double* R1 = fac + FL.R1;
+    for (int i = 0; i < n; i++)
+        for (int j = 0; j < n; j++) {
+            double s = 0.0;
+            if (j >= i) for (int k = i; k <= j; k++) s = fma(M[i * n + k], R1[k * n + j], s);
+            fac[FL.R + i * n + j] = s;
+        }
+    double* qtf = fac + FL.QTF;
+    for (int i = 0; i < n; i++) {
+        double s = 0.0;
+        for (int k = 0; k < i; k++) s = fma(M[k * n + i], qtf[k], s);
+        qtf[i] = (qtf[i] - s) / M[i * n + i];
+    }
+    fac[FL.INFO] = 0.0;
+    return 0;
+}
+
+int blsq_tall_sumsq(int64_t m, const double* f, double*, double* out, void*) {
+    double s = 0.0;
+    for (int64_t i = 0; i < m; i++) s = fma(f[i], f[i], s);
+    out[0] = s;
+    return 0;
+}
+
+int blsq_tall_layout(int n, int64_t* out) {
+    if (n < 2 || n > BLSQ_MAX_TALL_N) return BLSQ_E_UNSUPPORTED;
+    const TallLayout L(n);
+    const FacLayout FL(n);
+    out[0] = L.SIZE;  out[1] = L.ISIZE; out[2] = L.X;    out[3] = L.XNEW;
+    out[4] = TS_OBJ;  out[5] = TS_DELTA; out[6] = TS_GNORM; out[7] = L.ONB;
+    out[8] = FL.SIZE; out[9] = FL.R;    out[10] = FL.QTF; out[11] = FL.G;
+    out[12] = FL.OBJ; out[13] = FL.INFO; out[14] = FL.RINVP; out[15] = L.SCALE;
+    return 0;
+}
+
+int blsq_tall_round(int method, int phase, int n, int64_t m_total, int nranks,
+                    const double* ssq_parts, const double* fac, const double* x0,
+                    const double* lb, const double* ub, const double* scaling, double ftol,
+                    double xtol, double gtol, int max_nfev, int first, int new_lin,
+                    double* state, int32_t* istate, double*, void*) {
+    if (n < 2 || n > BLSQ_MAX_TALL_N) return BLSQ_E_UNSUPPORTED;
+    TallParams P;
+    P.ftol = ftol; P.xtol = xtol; P.gtol = gtol;
+    P.max_nfev = max_nfev; P.m = (double)m_total;
+    P.jac_scaling = scaling ? 0 : 1; P.n = n; P.method = method;
+    std::vector<double> red(128);
+    std::vector<int> ints(5 * n + 1 + 64);
+    Blk B;
+    B.tid = 0; B.nt = 1; B.lane = 0; B.warp = 0; B.nwarps = 1; B.lanes = 1;
+    B.red = red.data(); B.ired = ints.data() + 5 * n + 1;
+    if (phase == 0) { tall_init(B, method, n, x0, lb, ub, state, istate); return 0; }
+    if (phase == 1) {
+        double obj_new = 0.0;
+        for (int r = 0; r < nranks; r++) obj_new += ssq_parts[r];
+        tall_judge(B, P, obj_new, first, lb, ub, state, istate);
+        return 0;
+    }
+    std::vector<double> vec(TallWork::doubles(n)), rowbuf(n), A((size_t)n * n);
+    TallWork W;
+    W.carve(vec.data(), n);
+    W.rowbuf = rowbuf.data();
+    W.hits = ints.data(); W.flags = ints.data() + n; W.fr = ints.data() + 2 * n;
+    W.marks = ints.data() + 3 * n; W.prog = ints.data() + 4 * n;
+    W.A = A.data();
+    for (int i = 0; i < n; i++) { W.lb[i] = lb[i]; W.ub[i] = ub[i]; }
+    if (method == BLSQ_METHOD_TRF)
+        tall_trf_propose(B, P, W, fac, x0, scaling, first, new_lin, A.data(), state, istate);
+    else
+        tall_dogbox_propose(B, P, W, fac, x0, scaling, first, new_lin, A.data(), state, istate);
+    return 0;
+}
+
+}  // extern "C"

@@ -8,12 +8,14 @@ from bounded_lsq_b200._lib import Lib
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "host_emul", "emul.cpp")
 OUT = os.path.join(HERE, "host_emul", "libblsq_hostemul.so")
-CORE = os.path.join(os.path.dirname(HERE), "bounded_lsq_b200", "csrc",
-                    "blsq_core.cuh")
+_CSRC = os.path.join(os.path.dirname(HERE), "bounded_lsq_b200", "csrc")
+CORE = os.path.join(_CSRC, "blsq_core.cuh")
+TALL = [os.path.join(_CSRC, "blsq_tall_core.cuh"),
+        os.path.join(_CSRC, "blsq_tall_common.cuh")]
 
 
 def build():
-    deps = [SRC, CORE]
+    deps = [SRC, CORE] + TALL
     if os.path.exists(OUT) and all(os.path.getmtime(OUT) >= os.path.getmtime(d)
                                    for d in deps):
         return OUT

@@ -49,3 +49,10 @@ def test_per_problem_bounds(lib):
 def test_corpus_single(lib):
     st = cases.check_corpus_single(lib, DEV)
     assert st["exact_status"] >= 60
+
+
+@pytest.mark.parametrize("tag,method", [("a", "trf"), ("a", "dogbox"),
+                                        ("c", "trf"), ("c", "dogbox"),
+                                        ("d", "trf"), ("d", "dogbox")])
+def test_tall_golden(lib, tag, method):
+    print(cases.check_tall_golden(lib, torch.device("cpu"), tag, method))

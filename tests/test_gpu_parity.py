@@ -141,3 +141,26 @@ def test_fused_model_callbacks_bit_identical(lib, dev):
                                args=(PerProblem(y),))
     assert cases.bits(r1.x.cpu().numpy(), r2.x.cpu().numpy())
     assert cases.bits(r1.nfev.cpu().numpy(), r2.nfev.cpu().numpy())
+
+
+# ------------------------------------------------------------------ tall --
+
+@pytest.mark.parametrize("tag", ["a", "b", "c", "d"])
+@pytest.mark.parametrize("method", ["trf", "dogbox"])
+def test_tall_golden(lib, dev, tag, method):
+    """One tall problem (CholeskyQR2 Gram kernels + the n x n tail kernel)
+    against the unmodified reference's trf / dogbox on the same data."""
+    print(tag, method, cases.check_tall_golden(lib, dev, tag, method))
+
+
+def test_tall_factor_matches_qr(lib, dev):
+    """R, Q^T f, g of the tall factorisation against torch.linalg.qr at sizes
+    and shapes the golden problems do not cover (ragged m, n not a multiple of
+    8, a rank-deficient Jacobian)."""
+    cases.check_tall_factor(lib, dev)
+
+
+def test_tall_large_properties(lib, dev):
+    """m = 4M rows (no oracle at this size): the solve terminates feasible,
+    and R^T R = J^T J, R^T (Q^T f) = J^T f hold to rounding for the factor."""
+    cases.check_tall_large(lib, dev)

@@ -165,13 +165,15 @@ def test_batched_samples(golden_dir, fname, wl, method, fd):
 def test_tall_small(golden_dir):
     z = _load(golden_dir, "tall.npz")
     for meta in json.loads(str(z["meta"])):
-        if meta["tag"] != "a":
-            continue                       # 'b' (m=20000, n=64) is the GPU case
-        wl = TallLinExp(meta["m"], meta["n"], seed=meta["seed"])
-        assert _bits(np.float64(np.sum(wl.y)), z["a_y_checksum"])
+        tag = meta["tag"]
+        if tag not in ("a", "c"):
+            continue                 # b, d (m=20000, n=64) are host-emul / GPU cases
+        kw = {} if meta.get("x0_tail") is None else dict(x0_tail=meta["x0_tail"])
+        wl = TallLinExp(meta["m"], meta["n"], seed=meta["seed"], **kw)
+        assert _bits(np.float64(np.sum(wl.y)), z[tag + "_y_checksum"])
         res, trials = _run_oracle(meta["method"], wl.fun_np, wl.jac_np, wl.x0,
                                   wl.lb, wl.ub)
-        pre = f"a_{meta['method']}_"
+        pre = f"{tag}_{meta['method']}_"
         _check_against(z[pre + "x"], z[pre + "mask"], z[pre + "trials"],
                        z[pre + "scalars"], res, trials, pre)
 
