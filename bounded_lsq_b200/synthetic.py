@@ -198,3 +198,39 @@ class TallLinExp:
         J[:, k + 2] = e2
         J[:, k + 3] = -x[k + 2] * t * e2
         return J
+
+
+class TallLinExpDevice:
+    """The C4/C5 workload generated ON the device (bench.py): same model family
+    as TallLinExp, rows drawn with a torch generator so that 16M x 64 need not
+    pass through host memory.  ``rows`` is this rank's share; ``seed`` should
+    differ per rank."""
+
+    def __init__(self, rows, n, device, seed=0, noise=0.01,
+                 x0_tail=(0.5, 1.0, 0.5, 1.0), lb=-0.5, ub=5.0):
+        assert n >= 6 and n % 2 == 0
+        self.m, self.n, self.k = rows, n, n - 4
+        k = self.k
+        g = torch.Generator(device=device).manual_seed(1000 + seed)
+        f64 = torch.float64
+        self.A_t = torch.randn((rows, k), dtype=f64, device=device, generator=g)
+        self.t_t = torch.rand(rows, dtype=f64, device=device, generator=g)
+        rng = np.random.default_rng(12345)              # shared by all ranks
+        self.x_true = np.concatenate([rng.uniform(-1.0, 1.0, k), [1.0, 2.0, 0.5, 3.0]])
+        xt = torch.as_tensor(self.x_true, device=device)
+        self.y_t = torch.zeros(rows, dtype=f64, device=device)
+        self.y_t = self.fun_t(xt) + noise * torch.randn(rows, dtype=f64, device=device,
+                                                        generator=g)
+        self.x0 = np.concatenate([np.full(k, 0.1), list(x0_tail)])
+        self.lb = np.full(n, float(lb))
+        self.ub = np.full(n, float(ub))
+        self.J_t = torch.empty((rows, n), dtype=f64, device=device)
+        self.J_t[:, :k] = self.A_t
+
+    def load(self, A, t, y):
+        """Replace the data (e2e: fresh copies from pinned host buffers)."""
+        self.A_t, self.t_t, self.y_t = A, t, y
+        self.J_t[:, :self.k] = A
+
+    fun_t = TallLinExp.fun_t
+    jac_t = TallLinExp.jac_t

@@ -156,7 +156,10 @@ def solve_tall(lib, method, fun, jac, x0, lb, ub, ftol, xtol, gtol, max_nfev,
         e1.record()
         timers.setdefault(kind, []).append((e0, e1))
 
+    launches = [0]
+
     def round_(phase, first, new_lin, parts=None, m_total=0):
+        launches[0] += 1
         lib.call("blsq_tall_round", meth, phase, n, m_total, nranks,
                  None if parts is None else parts.data_ptr(), fac.data_ptr(),
                  x0.data_ptr(), lb.data_ptr(), ub.data_ptr(), sc_ptr,
@@ -167,6 +170,7 @@ def solve_tall(lib, method, fun, jac, x0, lb, ub, ftol, xtol, gtol, max_nfev,
     def factorise(J, f):
         m_loc = J.shape[0]
         for p in (1, 2):
+            launches[0] += 3                    # gram + reduce + factor
             t0 = tick()
             lib.call("blsq_tall_gram", p, m_loc, n, J.data_ptr(), f.data_ptr(),
                      fac[lay["rinvp"]:].data_ptr(), gwork.data_ptr(),
@@ -190,6 +194,7 @@ def solve_tall(lib, method, fun, jac, x0, lb, ub, ftol, xtol, gtol, max_nfev,
             m_total = gather.sum_int(f_new.shape[0], dev)
         elif f_cur is not None and f_new.shape != f_cur.shape:
             raise RuntimeError("`fun` changed its number of residuals")
+        launches[0] += 2
         t0 = tick()
         lib.call("blsq_tall_sumsq", f_new.shape[0], f_new.data_ptr(),
                  swork.data_ptr(), ssq.data_ptr(), st)
@@ -256,4 +261,6 @@ def solve_tall(lib, method, fun, jac, x0, lb, ub, ftol, xtol, gtol, max_nfev,
         nfev=ist[1], njev=ist[2], status=ist[0], x_covariance=None)
     res.message = TERMINATION_MESSAGES[res.status]
     res.success = res.status > 0
+    res.kernel_launches = launches[0]
+    res.m_total = m_total
     return res
