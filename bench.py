@@ -277,12 +277,16 @@ def run_tall(args, w):
     lb = torch.as_tensor(wl.lb, device=dev)
     ub = torch.as_tensor(wl.ub, device=dev)
     opts = {}
+    fun, jac = wl.fun_t, wl.jac_t
+    if args.callbacks == "fused":
+        from bounded_lsq_b200 import models as fused
+        fun, jac = fused.tall_callbacks(wl)
 
     def solve(timers=None):
         o = dict(opts)
         if timers is not None:
             o["timers"] = timers
-        return least_squares(wl.fun_t, x0, jac=wl.jac_t, bounds=(lb, ub),
+        return least_squares(fun, x0, jac=jac, bounds=(lb, ub),
                              method=w["method"], options=o)
 
     def barrier():
@@ -374,6 +378,7 @@ def run_tall(args, w):
         "data": "synthetic",
         "config": {"workload": w["desc"], "rows_total": m_total,
                    "rows_per_gpu": rows, "n": n, "method": w["method"],
+                   "callbacks": args.callbacks,
                    "step": "one complete TRF solve from x0; an iteration = one "
                            "accepted step (Jacobian + CholeskyQR2 + its trials)",
                    "iterations_per_step": its / args.steps,

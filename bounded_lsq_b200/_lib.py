@@ -12,7 +12,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libblsq_b200.so")
+# BLSQ_B200_LIB: tuning builds (tools/build_variants.sh); default = in-tree
+LIB_PATH = os.environ.get("BLSQ_B200_LIB") or os.path.join(_HERE, "libblsq_b200.so")
 
 _p = C.c_void_p
 _i = C.c_int
@@ -39,7 +40,10 @@ SIGNATURES = {
     "blsq_count_running": [_l, _p, _p, _p, _p],
     "blsq_model_expdecay2": [_l, _p, _i, _p, _p, _p, _p, _p, _p],
     "blsq_model_gausspeak": [_l, _p, _i, _p, _p, _p, _p, _p],
-    "blsq_tall_gram": [_i, _l, _i, _p, _p, _p, _p, _p, _p],
+    "blsq_model_linexp_fun": [_l, _i, _p, _p, _p, _p, _p, _p],
+    "blsq_model_linexp_jac": [_l, _i, _p, _p, _p, _p],
+    "blsq_tall_gram": [_i, _l, _i, _p, _p, _p, _i, _p, _p, _p],
+    "blsq_tall_sample_stride": [_l, _i],
     "blsq_tall_factor": [_i, _i, _i, _l, _p, _p, _p],
     "blsq_tall_sumsq": [_l, _p, _p, _p, _p],
     "blsq_tall_layout": [_i, _p],
@@ -82,7 +86,7 @@ class Lib:
         self._dll.blsq_error_string.restype = C.c_char_p
         self._dll.blsq_error_string.argtypes = [_i]
         for name in ("blsq_tall_gram_work_size", "blsq_tall_fac_size",
-                     "blsq_tall_state_size"):
+                     "blsq_tall_record_size"):
             if hasattr(self._dll, name):
                 f = getattr(self._dll, name)
                 f.argtypes = [_i]
@@ -137,15 +141,16 @@ class Lib:
         return dict(zip(keys, list(out)))
 
     def tall_layout(self, n):
-        out = (C.c_int64 * 16)()
+        out = (C.c_int64 * 17)()
         rc = self._fn["blsq_tall_layout"](n, C.cast(out, _p))
         if rc != 0:
             raise BlsqError(f"blsq_tall_layout({n}) failed: {rc}")
         keys = ("state_size", "istate_size", "x", "x_new", "obj", "delta",
                 "gnorm", "on_bound", "fac_size", "R", "qtf", "g", "fobj",
-                "info", "rinvp", "scale")
+                "info", "rinvp", "scale", "refine")
         d = dict(zip(keys, list(out)))
         d["gram_work"] = int(self._dll.blsq_tall_gram_work_size(n))
+        d["record"] = int(self._dll.blsq_tall_record_size(n))
         return d
 
     def lin_record_size(self, n):

@@ -48,6 +48,69 @@ gausspeak_kernel(int64_t A, const int64_t* __restrict__ idx, int m,
            __ldcs(y + pid * m + r);
 }
 
+
+// ---- tall workload (configs C4/C5): k = n - 4 linear columns + 2 exponentials --
+// The Jacobian buffer J (m, n) holds the constant design matrix A in its
+// first k columns, so the residual kernel reads A from there:
+//   f = J[:, :k] x[:k] + x_k e^{-x_{k+1} t} + x_{k+2} e^{-x_{k+3} t} - y
+// A warp takes 32 consecutive rows: each half warp streams 16 of them (16
+// lanes per row, 16-byte loads, shuffle reduction, lane i keeps the sum of row
+// i), then all 32 lanes evaluate the exponentials of their own row at once.
+__global__ void __launch_bounds__(256)
+linexp_fun_kernel(int64_t m, int n, const double* __restrict__ J,
+                  const double* __restrict__ t, const double* __restrict__ y,
+                  const double* __restrict__ x, double* __restrict__ F) {
+    __shared__ double xs[256];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) xs[i] = x[i];
+    __syncthreads();
+    const int k = n - 4;
+    const int lane = threadIdx.x & 31, l16 = lane & 15, half = lane >> 4;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const double xk = xs[k], xk1 = xs[k + 1], xk2 = xs[k + 2], xk3 = xs[k + 3];
+    for (int64_t base = warp * 32; base < m; base += nwarp * 32) {
+        double mine = 0.0;
+#pragma unroll 4
+        for (int it = 0; it < 16; it++) {
+            const int64_t r = base + half * 16 + it;
+            double s = 0.0;
+            if (r < m) {
+                const double* row = J + r * n;
+                for (int c = 2 * l16; c < k; c += 32) {
+                    const double2 a = __ldcs(reinterpret_cast<const double2*>(row + c));
+                    s = fma(a.x, xs[c], s);
+                    s = fma(a.y, xs[c + 1], s);
+                }
+            }
+#pragma unroll
+            for (int off = 8; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off, 16);
+            if (l16 == it) mine = s;
+        }
+        const int64_t r = base + lane;
+        if (r < m) {
+            const double tr = t[r];
+            F[r] = mine + xk * exp(-xk1 * tr) + xk2 * exp(-xk3 * tr) - y[r];
+        }
+    }
+}
+
+// J[:, k..k+3] = [e1, -x_k t e1, e2, -x_{k+2} t e2]; the first k columns stay
+__global__ void __launch_bounds__(256)
+linexp_jac_kernel(int64_t m, int n, double* __restrict__ J, const double* __restrict__ t,
+                  const double* __restrict__ x) {
+    const int k = n - 4;
+    const double xk = x[k], xk1 = x[k + 1], xk2 = x[k + 2], xk3 = x[k + 3];
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < m; r += stride) {
+        const double tr = t[r];
+        const double e1 = exp(-xk1 * tr);
+        const double e2 = exp(-xk3 * tr);
+        double2* jp = reinterpret_cast<double2*>(J + r * n + k);
+        jp[0] = make_double2(e1, -xk * tr * e1);
+        jp[1] = make_double2(e2, -xk2 * tr * e2);
+    }
+}
+
 }  // namespace
 
 extern "C" {
@@ -74,6 +137,29 @@ int blsq_model_gausspeak(int64_t A, const int64_t* idx, int m, const double* t,
     if (blocks > 0x7fffffff) return BLSQ_E_UNSUPPORTED;
     gausspeak_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
         A, idx, m, t, X, y, F);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : (int)e;
+}
+
+
+int blsq_model_linexp_fun(int64_t m, int n, const double* J, const double* t,
+                          const double* y, const double* x, double* F, void* stream) {
+    if (m < 0 || n < 6 || n > 256 || (n & 1) || !J || !t || !y || !x || !F) return BLSQ_E_BADARG;
+    if (m == 0) return 0;
+    int64_t blocks = (m + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    linexp_fun_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(m, n, J, t, y, x, F);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : (int)e;
+}
+
+int blsq_model_linexp_jac(int64_t m, int n, double* J, const double* t, const double* x,
+                          void* stream) {
+    if (m < 0 || n < 6 || n > 256 || (n & 1) || !J || !t || !x) return BLSQ_E_BADARG;
+    if (m == 0) return 0;
+    int64_t blocks = (m + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    linexp_jac_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(m, n, J, t, x);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : (int)e;
 }

@@ -22,11 +22,11 @@ inline BLSQ_TALL_HD int nb_for(int n) {
 }
 
 // fac (doubles):  R1 | R | scratch (n*n each) | Q^T f (n) | g (n) | f.f | info |
-//                 shift1, shift2 |
+//                 shift1, shift2 | refine |
 //                 R1^-1 in DMMA-fragment order (64 doubles per upper 8x8 block)
 struct FacLayout {
     int n, nb;
-    int64_t n2, R1, R, SCR, QTF, G, OBJ, INFO, SHIFT, RINVP, SIZE;
+    int64_t n2, R1, R, SCR, QTF, G, OBJ, INFO, SHIFT, REFINE, RINVP, SIZE;
     BLSQ_TALL_HD explicit FacLayout(int n_) : n(n_), nb(nb_for(n_)) {
         n2 = (int64_t)n * n;
         R1 = 0;
@@ -37,7 +37,8 @@ struct FacLayout {
         OBJ = G + n;
         INFO = OBJ + 1;
         SHIFT = INFO + 1;                 // diagonal shifts used by pass 1, 2
-        RINVP = (SHIFT + 2 + 1) & ~(int64_t)1;
+        REFINE = SHIFT + 2;               // 1: cond(J R1^-1) too large, run another pass
+        RINVP = (REFINE + 1 + 1) & ~(int64_t)1;
         SIZE = RINVP + (int64_t)nb * (nb + 1) / 2 * 64;
     }
 };

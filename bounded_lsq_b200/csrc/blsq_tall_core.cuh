@@ -35,7 +35,8 @@ using namespace blsq;
 // ---- state records -----------------------------------------------------------
 enum { TS_OBJ = 0, TS_DELTA, TS_ALPHA, TS_PRED, TS_CORR, TS_NSTEPH, TS_NSTEP, TS_GNORM,
        TS_NSCAL = 16 };
-enum { TI_STATUS = 0, TI_NFEV, TI_NJEV, TI_ACCEPT, TI_PENDING, TI_TRHIT, TI_NSCAL = 8 };
+enum { TI_STATUS = 0, TI_NFEV, TI_NJEV, TI_ACCEPT, TI_PENDING, TI_TRHIT, TI_SWEEPS,
+       TI_NSCAL = 8 };
 
 struct TallLayout {
     int n;
@@ -264,31 +265,64 @@ BLSQ_HD void tall_build_quadratic_1d(const Blk& B, const double* R, const TallWo
 }
 
 // ---- one-sided Jacobi on the rows of A (n x n) with the same rotations on b ----
-// Round-robin ordering: in step st of a sweep the N/2 pairs are disjoint, one
-// warp per pair.  Rows of A -> s_j v_j^T, b -> U^T b (see jacobi_rows in
-// blsq_core.cuh).
-BLSQ_HD bool jacobi_pair(const Blk& B, double* A, double* b, int n, int p, int q) {
+// Round-robin ordering: in step st of a sweep the N/2 pairs are disjoint.  A
+// pair is handled by a GROUP of G lanes (G = 4..32, about n/8: each lane owns
+// ~8 elements of both rows, so the three dot products cost log2(G) shuffle
+// rounds), 32/G pairs per warp; only the warps that have pairs take part and
+// they synchronise on a named barrier, the rest of the block waits at the end.
+// Rows of A -> s_j v_j^T, b -> U^T b (see jacobi_rows in blsq_core.cuh).
+BLSQ_HD double group_sum(double v, int G) {
+#if BLSQ_TALL_DEV
+    for (int off = G >> 1; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+#endif
+    return v;
+}
+
+// `valid` = this group has a real pair (all lanes of the warp call this).
+BLSQ_HD bool jacobi_pair(double* A, double* b, int n, int p, int q, bool valid, int gl, int G) {
     double* ap = A + (size_t)p * n;
     double* aq = A + (size_t)q * n;
     double al = 0.0, be = 0.0, ga = 0.0;
-    for (int i = B.lane; i < n; i += B.lanes) {
-        const double x = ap[i], y = aq[i];
-        al = fma(x, x, al);
-        be = fma(y, y, be);
-        ga = fma(x, y, ga);
+    if (valid) {
+        for (int i = gl; i < n; i += G) {
+            const double x = ap[i], y = aq[i];
+            al = fma(x, x, al);
+            be = fma(y, y, be);
+            ga = fma(x, y, ga);
+        }
     }
-    al = warp_sum(al); be = warp_sum(be); ga = warp_sum(ga);
-    if (ga == 0.0 || ga * ga <= (EPS * EPS) * (al * be)) return false;
-    const double zeta = (be - al) / (2.0 * ga);
-    const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(fma(zeta, zeta, 1.0)));
-    const double c = 1.0 / sqrt(fma(t, t, 1.0));
+    al = group_sum(al, G); be = group_sum(be, G); ga = group_sum(ga, G);
+    if (!valid || ga == 0.0 || ga * ga <= (EPS * EPS) * (al * be)) return false;
+    // tan of the rotation angle, t = sign(zeta) / (|zeta| + sqrt(1 + zeta^2)) with
+    // zeta = (be - al) / (2 ga), rearranged to one division and one square root
+    const double dd = be - al;
+    const double g2 = 2.0 * ga;
+#if BLSQ_TALL_DEV
+    // The angle only has to be accurate enough to make progress (Jacobi is
+    // self correcting; the convergence test above is in double): evaluate the
+    // tangent in single precision after scaling (dd, g2) by a power of two,
+    // then build an exactly orthogonal (c, sn) pair in double.  This takes the
+    // double division and square root off the per-step critical path.
+    const double big = fmax(fabs(dd), fabs(g2));
+    const int ex = (__double2hiint(big) >> 20) & 0x7ff;
+    const double scl = __hiloint2double((2046 - ex) << 20, 0);      // 2^(1023 - ex)
+    const float df = (float)(dd * scl), gf = (float)(g2 * scl);
+    float tf = copysignf(gf, df * gf) / (fabsf(df) + sqrtf(fmaf(df, df, gf * gf)));
+    if (df == 0.0f) tf = copysignf(1.0f, gf);
+    const double t = (ex == 0 || ex == 0x7ff) ? copysign(g2, dd * ga) /
+                         (fabs(dd) + sqrt(fma(dd, dd, g2 * g2)))
+                                              : (double)tf;
+#else
+    const double t = copysign(g2, dd * ga) / (fabs(dd) + sqrt(fma(dd, dd, g2 * g2)));
+#endif
+    const double c = rsqrt_d(fma(t, t, 1.0));
     const double sn = c * t;
-    for (int i = B.lane; i < n; i += B.lanes) {
+    for (int i = gl; i < n; i += G) {
         const double x = ap[i], y = aq[i];
         ap[i] = fma(c, x, -(sn * y));
         aq[i] = fma(sn, x, c * y);
     }
-    if (B.lane == 0) {
+    if (gl == 0) {
         const double bp = b[p], bq = b[q];
         b[p] = fma(c, bp, -(sn * bq));
         b[q] = fma(sn, bp, c * bq);
@@ -296,23 +330,67 @@ BLSQ_HD bool jacobi_pair(const Blk& B, double* A, double* b, int n, int p, int q
     return true;
 }
 
-BLSQ_HD void tall_jacobi(const Blk& B, double* A, double* b, int n) {
-    if (n < 2) return;
+// Returns the number of sweeps (diagnostics: istate[TI_SWEEPS]).
+BLSQ_HD int tall_jacobi(const Blk& B, double* A, double* b, int n) {
+    if (n < 2) return 0;
     const int N = (n + 1) & ~1;          // players; index n (if any) is a bye
-    for (int sweep = 0; sweep < 60; sweep++) {
-        bool rotated = false;
-        for (int st = 0; st < N - 1; st++) {
-            for (int k = B.warp; k < N / 2; k += B.nwarps) {
-                int p, q;
-                if (k == 0) { p = N - 1; q = st; }
-                else { p = (st + k) % (N - 1); q = (st - k + (N - 1)) % (N - 1); }
-                if (p > q) { const int tmp = p; p = q; q = tmp; }
-                if (q < n) rotated = jacobi_pair(B, A, b, n, p, q) || rotated;
+    const int npairs = N / 2;
+#if BLSQ_TALL_DEV
+    int G = 4;
+    while (G < 32 && G * 8 < n) G <<= 1;
+    const int ppw = 32 / G;                              // pairs per warp
+    int nact = (npairs + ppw - 1) / ppw;                 // warps that have pairs
+    if (nact > B.nwarps) nact = B.nwarps;
+    const int gl = B.lane & (G - 1);
+    const int slot = B.warp * ppw + B.lane / G;          // first pair of this group
+    const int nslots = nact * ppw;
+    volatile int* flag = B.ired;                         // [0], [1]: "rotated" per sweep parity
+    if (B.tid < 2) flag[B.tid] = 0;
+    __syncthreads();
+#else
+    const int G = 1, gl = 0, slot = 0, nslots = 1, nact = 1;
+#endif
+    int sweep = 0;
+    int sweeps = 0;
+    if (B.warp < nact) {
+        for (; sweep < 60; sweep++) {
+            bool rotated = false;
+            for (int st = 0; st < N - 1; st++) {
+                for (int k0 = 0; k0 < npairs; k0 += nslots) {
+                    const int k = k0 + slot;
+                    int p = N - 1, q = st;
+                    if (k != 0) {
+                        p = st + k; if (p >= N - 1) p -= N - 1;
+                        q = st - k; if (q < 0) q += N - 1;
+                    }
+                    if (p > q) { const int tmp = p; p = q; q = tmp; }
+                    const bool valid = k < npairs && q < n;
+                    rotated = jacobi_pair(A, b, n, valid ? p : 0, valid ? q : 0, valid, gl, G) ||
+                              rotated;
+                }
+#if BLSQ_TALL_DEV
+                asm volatile("bar.sync 1, %0;" ::"r"(nact * 32) : "memory");
+                // everyone has read last sweep's flag before this barrier
+                if (st == 0 && B.tid == 0) flag[(sweep + 1) & 1] = 0;
+#endif
             }
-            B.sync();
+#if BLSQ_TALL_DEV
+            if (rotated) flag[sweep & 1] = 1;
+            asm volatile("bar.sync 1, %0;" ::"r"(nact * 32) : "memory");
+            rotated = flag[sweep & 1] != 0;
+#endif
+            if (!rotated) break;
         }
-        if (!blk_any(B, rotated)) break;
+        sweeps = sweep + 1;
+#if BLSQ_TALL_DEV
+        if (B.tid == 0) B.ired[2] = sweeps;
+#endif
     }
+    B.sync();
+#if BLSQ_TALL_DEV
+    sweeps = B.ired[2];
+#endif
+    return sweeps;
 }
 
 // Fold row k of diag(sqrt(diag_h)) into the upper triangle A (and [b; 0]) by
@@ -381,8 +459,8 @@ BLSQ_HD void tall_fold(const Blk& B, double* A, double* b, const double* diag_h,
 // Factorisation of the hat-space augmented matrix (trf.py:264-274) from the
 // triangle: A = R diag(d) with diag(sqrt(diag_h)) folded in, then Jacobi.
 // Outputs (global state): S, SUF = S * (U^T f_aug), VT (row j = v_j).
-BLSQ_HD void tall_hat_svd(const Blk& B, const double* R, const TallWork& W, double* A,
-                          double* S, double* SUF, double* VT) {
+BLSQ_HD int tall_hat_svd(const Blk& B, const double* R, const TallWork& W, double* A,
+                         double* S, double* SUF, double* VT) {
     const int n = W.n;
     for (int e = B.tid; e < n * n; e += B.nt) {
         const int i = e / n, j = e % n;
@@ -391,7 +469,7 @@ BLSQ_HD void tall_hat_svd(const Blk& B, const double* R, const TallWork& W, doub
     for (int i = B.tid; i < n; i += B.nt) W.b[i] = W.qtf[i];
     B.sync();
     tall_fold(B, A, W.b, W.diag_h, n, W.rowbuf, W.prog, W.flags);
-    tall_jacobi(B, A, W.b, n);
+    const int sweeps = tall_jacobi(B, A, W.b, n);
     for (int j = B.warp; j < n; j += B.nwarps) {
         double nn = 0.0;
         for (int i = B.lane; i < n; i += B.lanes) nn = fma(A[(size_t)j * n + i], A[(size_t)j * n + i], nn);
@@ -402,6 +480,7 @@ BLSQ_HD void tall_hat_svd(const Blk& B, const double* R, const TallWork& W, doub
         if (B.lane == 0) { S[j] = sj; SUF[j] = sj * W.b[j]; }
     }
     B.sync();
+    return sweeps;
 }
 
 // trust_region.py:47-53 over the block
@@ -667,7 +746,10 @@ BLSQ_HD void tall_trf_propose(const Blk& B, const TallParams& P, const TallWork&
         B.sync();
         return;
     }
-    if (new_lin) tall_hat_svd(B, R, W, A, S, SUF, VT);
+    if (new_lin) {
+        const int sweeps = tall_hat_svd(B, R, W, A, S, SUF, VT);
+        if (B.tid == 0) ist[TI_SWEEPS] = sweeps;
+    }
     double theta = 1.0 - g_norm;
     if (theta < 0.995) theta = 0.995;
 
@@ -878,7 +960,8 @@ BLSQ_HD void tall_dogbox_propose(const Blk& B, const TallParams& P, const TallWo
         }
         for (int i = B.tid; i < n; i += B.nt) W.b[i] = W.qtf[i];
         B.sync();
-        tall_jacobi(B, A, W.b, n);
+        const int sweeps = tall_jacobi(B, A, W.b, n);
+        if (B.tid == 0) ist[TI_SWEEPS] = sweeps;
         double smax2 = 0.0;
         for (int j = B.warp; j < n; j += B.nwarps) {
             double nn = 0.0;

@@ -1,9 +1,15 @@
 // Tall mode, the n x n factor step of CholeskyQR2 (one CTA, latency bound).
 //
-//   pass 1:  G = sum over ranks of J^T J  ->  R1 = chol(G) (upper), R1^-1,
-//            g = J^T f (trf.py:244 / dogbox.py:170), f.f
-//   pass 2:  G2 = sum over ranks of Y^T Y, Y = J R1^-1  ->  R2 = chol(G2),
-//            R = R2 R1  (J = Q R),  Q^T f = R2^-T (Y^T f)
+//   pass 1:  G = sum over ranks of J_s^T J_s (all rows, or a sample of the row
+//            tiles)  ->  R1 = chol(G) (upper), R1^-1: the preconditioner
+//   pass 2:  G2 = sum over ranks of Y^T Y, Y = J R1^-1 (every row)  ->
+//            R2 = chol(G2), R = R2 R1 (J = Q R), Q^T f = R2^-T (Y^T f),
+//            g = J^T f (trf.py:244 / dogbox.py:170), f.f; and the check that
+//            G2 is close enough to the identity for ONE Cholesky pass to be
+//            accurate (Gershgorin on the unit-diagonal scaling: off-diagonal
+//            row sums <= 1/2  =>  scaled condition number <= 3).  If
+//            not, fac.refine = 1 and the driver runs
+//   pass 3:  R1 <- R, R1^-1  (no Cholesky), then gram(2) + pass 2 again.
 //
 // The rank partials are summed in rank order, so every rank of a row-sharded
 // run computes bit-identical factors (no broadcast needed).
@@ -75,6 +81,19 @@ __device__ void inv_upper(const double* R, double* X, int n) {
     }
 }
 
+// dense upper-triangular X (n x n) -> the DMMA fragment order of pass 2
+__device__ void pack_rinv(const double* X, double* rinvp, int n, int nb) {
+    const int nblk = nb * (nb + 1) / 2;
+    for (int e = threadIdx.x; e < nblk * 64; e += blockDim.x) {
+        const int q = e >> 6, half = (e >> 5) & 1, lane = e & 31;
+        int kb = 0, qq = q;
+        while (qq >= nb - kb) { qq -= nb - kb; kb++; }
+        const int jb = kb + qq;
+        const int r = 8 * kb + 4 * half + (lane & 3), c = 8 * jb + (lane >> 2);
+        rinvp[e] = (r < n && c < n && c >= r) ? X[r * n + c] : 0.0;
+    }
+}
+
 __global__ void __launch_bounds__(FAC_THREADS, 1)
 tall_factor_kernel(int pass, int n, int nranks, int64_t gstride, const double* __restrict__ grams,
                    double* __restrict__ fac, int use_smem) {
@@ -91,8 +110,20 @@ tall_factor_kernel(int pass, int n, int nranks, int64_t gstride, const double* _
     double* info = fac + FL.INFO;
     double* rinvp = fac + FL.RINVP;
     double* shifts = fac + FL.SHIFT;
+    double* refine = fac + FL.REFINE;
     double* M = use_smem ? fsm : scratch;
 
+    if (pass == 3) {
+        // the factor found so far becomes the preconditioner of another pass
+        for (int e = tid; e < n2; e += nt) { R1[e] = R[e]; M[e] = R[e]; }
+        __syncthreads();
+        double* X = use_smem ? scratch : R;
+        inv_upper(M, X, n);
+        __syncthreads();
+        pack_rinv(X, rinvp, n, FL.nb);
+        if (tid == 0) { refine[0] = 0.0; info[0] = 0.0; }
+        return;
+    }
     // Cholesky of the rank-order sum of the records.  A rank-deficient (or
     // worse than ~1e7 conditioned) Jacobian makes a pivot collapse; the sweep
     // is then redone on G + shift*I, shift = 16 n eps max(diag G) (x10 per
@@ -105,19 +136,20 @@ tall_factor_kernel(int pass, int n, int nranks, int64_t gstride, const double* _
     double shift = 0.0;
     int bad = 0;
     for (int attempt = 0; attempt < 12; attempt++) {
-        for (int e = tid; e < n2 + n + 1; e += nt) {
+        const int nvec = (pass == 2 && attempt == 0) ? 2 * n + 1 : 0;
+        for (int e = tid; e < n2 + nvec; e += nt) {
             double s = 0.0;
             for (int r = 0; r < nranks; r++) s += grams[(size_t)r * gstride + e];
             if (e < n2) {
                 const int i = e / n, j = e % n;
                 if (i == j) { if (attempt == 0) diag0[i] = s; s += shift; }
                 M[e] = s;
-            } else if (attempt == 0) {
-                if (pass == 1) {
-                    if (e < n2 + n) g[e - n2] = s; else obj[0] = s;
-                } else if (e < n2 + n) {
-                    qtf[e - n2] = s;                 // Y^T f for now
-                }
+            } else if (e < n2 + n) {
+                qtf[e - n2] = s;                     // Y^T f for now
+            } else if (e == n2 + n) {
+                obj[0] = s;
+            } else {
+                g[e - n2 - n - 1] = s;
             }
         }
         __syncthreads();
@@ -127,13 +159,41 @@ tall_factor_kernel(int pass, int n, int nranks, int64_t gstride, const double* _
             dmax_s = d;
         }
         __syncthreads();
+        if (attempt == 0 && pass == 2) {
+            // is G2 close to (a multiple of) the identity?  Columns whose
+            // diagonal is at rounding level are the null directions of a rank
+            // deficient J (their Y column is noise): no pass can fix those,
+            // they are left out of the test.
+            const double tiny = 1e-8 * dmax_s;
+            int far = 0;
+            for (int i = tid; i < n; i += nt) {
+                if (!(diag0[i] > tiny)) continue;
+                double rs = 0.0;
+                for (int j = 0; j < n; j++) {
+                    if (j == i || !(diag0[j] > tiny)) continue;
+                    const double gij = (j > i) ? M[i * n + j] : M[j * n + i];
+                    rs += fabs(gij) / sqrt(diag0[i] * diag0[j]);
+                }
+                if (!(rs <= 0.5)) far = 1;
+            }
+            // (the spread of the diagonal itself does not matter: Gram and
+            // Cholesky errors scale with sqrt(G_ii G_jj) componentwise)
+            far = __syncthreads_or(far);
+            if (tid == 0) refine[0] = far ? 1.0 : 0.0;
+        }
+        __syncthreads();
         bad = chol_upper(M, diag0, n);
         if (!bad) break;
         if (!(dmax_s > 0.0) || dmax_s != dmax_s) break;      // zero or NaN Jacobian
         shift = (shift == 0.0) ? 16.0 * n * 2.220446049250313e-16 * dmax_s : shift * 10.0;
         __syncthreads();
     }
-    if (tid == 0) shifts[pass - 1] = shift;
+    if (tid == 0) {
+        shifts[pass - 1] = shift;
+        // a pivot that needed a shift means J itself is rank deficient:
+        // another pass cannot improve on that
+        if (pass == 2 && shift != 0.0) refine[0] = 0.0;
+    }
     if (bad) {
         if (tid == 0) info[0] = 1000.0 * pass + bad;
         return;
@@ -148,16 +208,7 @@ tall_factor_kernel(int pass, int n, int nranks, int64_t gstride, const double* _
         double* X = use_smem ? scratch : R;
         inv_upper(M, X, n);
         __syncthreads();
-        const int nb = FL.nb;
-        const int nblk = nb * (nb + 1) / 2;
-        for (int e = tid; e < nblk * 64; e += nt) {
-            const int q = e >> 6, half = (e >> 5) & 1, lane = e & 31;
-            int kb = 0, qq = q;
-            while (qq >= nb - kb) { qq -= nb - kb; kb++; }
-            const int jb = kb + qq;
-            const int r = 8 * kb + 4 * half + (lane & 3), c = 8 * jb + (lane >> 2);
-            rinvp[e] = (r < n && c < n && c >= r) ? X[r * n + c] : 0.0;
-        }
+        pack_rinv(X, rinvp, n, FL.nb);
         if (tid == 0) info[0] = 0.0;
         return;
     }
@@ -194,9 +245,9 @@ int64_t blsq_tall_fac_size(int n) {
 
 int blsq_tall_factor(int pass, int n, int nranks, int64_t gstride, const double* grams,
                      double* fac, void* stream) {
-    if ((pass != 1 && pass != 2) || nranks < 1 || !grams || !fac) return BLSQ_E_BADARG;
+    if (pass < 1 || pass > 3 || nranks < 1 || !fac || (pass != 3 && !grams)) return BLSQ_E_BADARG;
     if (n < 2 || n > 256) return BLSQ_E_UNSUPPORTED;
-    if (gstride < (int64_t)n * n + n + 1) return BLSQ_E_BADARG;
+    if (pass != 3 && gstride < (int64_t)n * n + 2 * n + 1) return BLSQ_E_BADARG;
     const int use_smem = n <= FAC_SMEM_MAX_N;
     const size_t smem = use_smem ? (size_t)n * n * 8 : 0;
     cudaError_t e = cudaFuncSetAttribute(tall_factor_kernel,

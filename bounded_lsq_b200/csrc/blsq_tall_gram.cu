@@ -104,11 +104,23 @@ struct Tri {
 };
 
 template <int NB> struct GramCfg;
-template <> struct GramCfg<2>  { static constexpr int T = 64, S = 4, CW = 4, ROLES = 1, CG = 2; static constexpr bool RINV_SMEM = true; };
-template <> struct GramCfg<4>  { static constexpr int T = 64, S = 4, CW = 8, ROLES = 1, CG = 4; static constexpr bool RINV_SMEM = true; };
-template <> struct GramCfg<8>  { static constexpr int T = 64, S = 4, CW = 8, ROLES = 2, CG = 8; static constexpr bool RINV_SMEM = true; };
-template <> struct GramCfg<16> { static constexpr int T = 64, S = 2, CW = 8, ROLES = 8, CG = 8; static constexpr bool RINV_SMEM = false; };
-template <> struct GramCfg<32> { static constexpr int T = 32, S = 2, CW = 8, ROLES = 8, CG = 8; static constexpr bool RINV_SMEM = false; };
+// T rows per tile, S1/S2 ring stages in pass 1/2, CW consumer warps, R1/R2
+// warp roles over the Gram blocks in pass 1/2, CG column blocks per phase-A
+// item, YB2: pass 2 double-buffers Y so that one block barrier per tile suffices
+#ifndef BLSQ_G8_CW          /* tuning knobs of the n = 64 kernels (tools/build_gram_variants.sh) */
+#define BLSQ_G8_CW 8
+#define BLSQ_G8_R1 2
+#define BLSQ_G8_R2 4
+#define BLSQ_G8_CG 8
+#define BLSQ_G8_S1 4
+#define BLSQ_G8_S2 3
+#define BLSQ_G8_YB2 true
+#endif
+template <> struct GramCfg<2>  { static constexpr int T = 64, S1 = 4, S2 = 4, CW = 4, R1 = 1, R2 = 1, CG = 2; static constexpr bool RINV_SMEM = true,  YB2 = true; };
+template <> struct GramCfg<4>  { static constexpr int T = 64, S1 = 4, S2 = 4, CW = 8, R1 = 1, R2 = 1, CG = 4; static constexpr bool RINV_SMEM = true,  YB2 = true; };
+template <> struct GramCfg<8>  { static constexpr int T = 64, S1 = BLSQ_G8_S1, S2 = BLSQ_G8_S2, CW = BLSQ_G8_CW, R1 = BLSQ_G8_R1, R2 = BLSQ_G8_R2, CG = BLSQ_G8_CG; static constexpr bool RINV_SMEM = true,  YB2 = BLSQ_G8_YB2; };
+template <> struct GramCfg<16> { static constexpr int T = 64, S1 = 2, S2 = 2, CW = 8, R1 = 8, R2 = 8, CG = 8; static constexpr bool RINV_SMEM = false, YB2 = false; };
+template <> struct GramCfg<32> { static constexpr int T = 32, S1 = 2, S2 = 2, CW = 8, R1 = 8, R2 = 8, CG = 8; static constexpr bool RINV_SMEM = false, YB2 = false; };
 
 // Shared-memory layout of one tile of T rows.  The tile is kept as four
 // QUARTERS of QR = T/4 consecutive rows, each quarter dense (row stride RS = n)
@@ -123,22 +135,52 @@ struct GramLayout {
     static constexpr int QR = C::T / 4;         // rows per quarter
     static constexpr int QS = QR * W + 4;       // quarter stride (doubles)
     static constexpr int NBLK = Tri<NB>::COUNT;
-    static constexpr int BPR = (NBLK + C::ROLES - 1) / C::ROLES;   // blocks per role
-    static constexpr int KS = C::CW / C::ROLES;                    // row split
+    // Blocks per role.  In pass 2 role 0 also accumulates Y^T f and J^T f
+    // (2 NB DFMAs per chunk = NB/4 DMMAs of pipe time), so it gets fewer blocks.
+    static constexpr int ROLES = (PASS == 2) ? C::R2 : C::R1;
+    static constexpr int FW = (PASS == 2) ? (NB + 3) / 4 : 0;
+    static constexpr int B0_ = (NBLK + FW) / ROLES - FW;
+    static constexpr int B0 = (ROLES == 1) ? NBLK : (B0_ < 1 ? 1 : B0_);         // role 0
+    static constexpr int BPR = (ROLES == 1) ? NBLK : (NBLK - B0 + ROLES - 2) / (ROLES - 1);
+    __host__ __device__ static constexpr int role_begin(int r) {
+        return r == 0 ? 0 : B0 + (r - 1) * BPR;
+    }
+    __host__ __device__ static constexpr int role_count(int r) {
+        return r == 0 ? B0
+                      : (role_begin(r) >= NBLK ? 0
+                                               : (role_begin(r) + BPR <= NBLK ? BPR
+                                                                              : NBLK - role_begin(r)));
+    }
+    static constexpr int MAXQ = B0 > BPR ? B0 : BPR;
+    static constexpr int KS = C::CW / ROLES;                       // row split
     static constexpr int THREADS = (C::CW + 1) * 32;
-    static constexpr int STAGE_DOUBLES = 4 * QS + C::T;            // tile + f
-    static constexpr int YBUF_DOUBLES = (PASS == 2) ? 4 * QS : 0;
+    static constexpr int S = (PASS == 2) ? C::S2 : C::S1;          // ring stages
+    static constexpr int STAGE_DOUBLES = 4 * QS + C::T;            // tile + f (pass 2)
+    static constexpr int YBUF_DOUBLES = (PASS == 2) ? (C::YB2 ? 8 : 4) * QS : 0;
     static constexpr int RINV_DOUBLES = (PASS == 2 && C::RINV_SMEM) ? NBLK * 64 : 0;
-    static constexpr int PER = NBLK * 64 + W + 2;                  // one warp copy (even: double2 stores)
+    static constexpr int PER = NBLK * 64 + 2 * W + 2;              // one warp copy (even: double2 stores)
     static constexpr int RED_DOUBLES = (KS > 1) ? KS * PER : 0;
-    static constexpr int RING_DOUBLES = C::S * STAGE_DOUBLES;
+    static constexpr int RING_DOUBLES = S * STAGE_DOUBLES;
     // the cross-warp reduction reuses the ring once the pipeline has drained
     static constexpr int BASE_DOUBLES = RING_DOUBLES > RED_DOUBLES ? RING_DOUBLES : RED_DOUBLES;
     static constexpr int MAIN_DOUBLES = BASE_DOUBLES + YBUF_DOUBLES + RINV_DOUBLES;
-    static constexpr size_t SMEM_BYTES = (size_t)MAIN_DOUBLES * 8 + 2 * C::S * 8 + 16;
-    // per-CTA partial record: G (W x W, upper blocks), g (W), f.f
-    static constexpr int REC = W * W + W + 2;
+    static constexpr size_t SMEM_BYTES = (size_t)MAIN_DOUBLES * 8 + 2 * S * 8 + 16;
+    // per-CTA partial record: G (W x W, upper blocks) | Y^T f (W) | f.f, pad |
+    // J^T f (W); the vectors and f.f are produced by pass 2 only
+    static constexpr int OFF_V1 = W * W, OFF_FF = W * W + W, OFF_V2 = W * W + W + 2;
+    static constexpr int REC = W * W + 2 * W + 2;
 };
+
+// Pass 1 may run on a SAMPLE of the tiles (it only has to deliver a
+// preconditioner R1 with cond(J R1^-1) = O(1); pass 2 sees every row and
+// blsq_tall_factor verifies the result): one tile out of every `sstride`
+// consecutive ones, at a hashed position inside the group.
+__device__ __forceinline__ int64_t sample_tile(int64_t j, int sstride) {
+    if (sstride <= 1) return j;
+    uint32_t h = (uint32_t)j * 2654435761u;
+    h ^= h >> 15;
+    return j * sstride + (int64_t)(h % (uint32_t)sstride);
+}
 
 template <int NB, int Q0, int... Qs>
 __device__ __forceinline__ void mma_role_blocks(double (&acc)[sizeof...(Qs)][2],
@@ -149,45 +191,50 @@ __device__ __forceinline__ void mma_role_blocks(double (&acc)[sizeof...(Qs)][2],
 
 // EXACT: n == 8*NB (no column padding, row stride is a compile-time constant)
 template <int NB, int PASS, bool EXACT, int ROLE>
-__device__ __forceinline__ void consumer_loop(int64_t m, const double* __restrict__ rinvp_g,
+__device__ __forceinline__ void consumer_loop(int64_t njobs, const double* __restrict__ rinvp_g,
                                               int n, double* smem, uint64_t* full,
                                               uint64_t* empty, double* __restrict__ rec) {
     typedef GramCfg<NB> C;
     typedef GramLayout<NB, PASS> L;
-    constexpr int T = C::T, S = C::S, CW = C::CW, W = L::W, QR = L::QR, QS = L::QS;
-    constexpr int Q0 = ROLE * L::BPR;
-    constexpr int NQ = (Q0 + L::BPR <= L::NBLK) ? L::BPR : (L::NBLK - Q0);
+    constexpr int T = C::T, S = L::S, CW = C::CW, W = L::W, QR = L::QR, QS = L::QS;
+    constexpr int Q0 = L::role_begin(ROLE);
+    constexpr int NQ = L::role_count(ROLE);
+    static_assert(NQ > 0, "every role must own at least one Gram block");
     constexpr int KS = L::KS;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int ks = warp / C::ROLES;
+    const int ks = warp / L::ROLES;
     const int lr = lane >> 2, lc = lane & 3;
     const int RS = EXACT ? W : n;               // row stride inside a quarter
 
-    double* ybuf = smem + L::BASE_DOUBLES;
-    const double* rinvp = C::RINV_SMEM ? (ybuf + L::YBUF_DOUBLES) : rinvp_g;
+    double* ybuf0 = smem + L::BASE_DOUBLES;
+    const double* rinvp = C::RINV_SMEM ? (ybuf0 + L::YBUF_DOUBLES) : rinvp_g;
+    int ypar = 0;
 
     double acc[NQ][2];
 #pragma unroll
     for (int q = 0; q < NQ; q++) { acc[q][0] = 0.0; acc[q][1] = 0.0; }
-    double gf[NB], ff = 0.0;
+    // pass 2, role 0: Y^T f, J^T f (trf.py:244 / dogbox.py:170) and f.f
+    double gf[NB], gj[NB], ff = 0.0;
 #pragma unroll
-    for (int b = 0; b < NB; b++) gf[b] = 0.0;
+    for (int b = 0; b < NB; b++) { gf[b] = 0.0; gj[b] = 0.0; }
 
-    const int64_t ntiles = (m + T - 1) / T;
     int stage = 0;
     uint32_t phase = 0;
-    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    for (int64_t t = blockIdx.x; t < njobs; t += gridDim.x) {
         mbar_wait(&full[stage], phase);
         const double* tj = smem + (size_t)stage * L::STAGE_DOUBLES;
         const double* tf = tj + 4 * QS;
+        double* ybuf = ybuf0 + (C::YB2 ? ypar * 4 * QS : 0);
         if (PASS == 2) {
             // ---- phase A: Y = tile * Rinv; a strip is 8 rows (two from each
             //      quarter), an item is a strip x CG column blocks ----
             constexpr int NSTRIP = T / 8;
             constexpr int NCG = NB / C::CG;
             constexpr int ITEMS = NSTRIP * NCG;
-            // everyone must be done reading ybuf of the previous tile
-            named_bar_sync(1, CW * 32);
+            // Everyone must be done reading this Y buffer.  Double buffered
+            // (YB2): its last readers were phase B two tiles ago, and every
+            // warp has passed the barrier below once since -> no barrier here.
+            if (!C::YB2) named_bar_sync(1, CW * 32);
             for (int it = warp; it < ITEMS; it += CW) {
                 const int strip = it % NSTRIP;
                 const int cg = (NCG == 1) ? 0 : it / NSTRIP;
@@ -230,11 +277,16 @@ __device__ __forceinline__ void consumer_loop(int64_t m, const double* __restric
                         }
                     }
                 }
+                // two 8-byte stores per block, the element order swapped on odd
+                // rows: the 16 lanes of a store phase then hit 32 distinct banks
+                // (a 16-byte store of the C fragment is 2-way conflicted here)
                 double* yrow = ybuf + (lr & 3) * QS + qrow * W + 2 * lc;
+                const int odd = lr & 1;
 #pragma unroll
                 for (int jj = 0; jj < C::CG; jj++) {
                     const int j = cg * C::CG + jj;
-                    *reinterpret_cast<double2*>(yrow + 8 * j) = make_double2(y[jj][0], y[jj][1]);
+                    yrow[8 * j + odd] = odd ? y[jj][1] : y[jj][0];
+                    yrow[8 * j + 1 - odd] = odd ? y[jj][0] : y[jj][1];
                 }
             }
             named_bar_sync(1, CW * 32);
@@ -250,24 +302,32 @@ __device__ __forceinline__ void consumer_loop(int64_t m, const double* __restric
             for (int b = 0; b < NB; b++)
                 frag[b] = (PASS == 2 || EXACT || 8 * b + lr < n) ? base[8 * b] : 0.0;
             mma_role_blocks<NB, Q0>(acc, frag, std::make_integer_sequence<int, NQ>{});
-            if (ROLE == 0) {
+            if (PASS == 2 && ROLE == 0) {
                 const double fk = tf[lc * QR + kc];
+                const double* rawb = tj + lc * QS + kc * RS + lr;
 #pragma unroll
-                for (int b = 0; b < NB; b++) gf[b] = fma(frag[b], fk, gf[b]);
+                for (int b = 0; b < NB; b++) {
+                    gf[b] = fma(frag[b], fk, gf[b]);
+                    const double raw = (EXACT || 8 * b + lr < n) ? rawb[8 * b] : 0.0;
+                    gj[b] = fma(raw, fk, gj[b]);
+                }
                 if (lr == 0) ff = fma(fk, fk, ff);
             }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[stage]);
         if (++stage == S) { stage = 0; phase ^= 1; }
+        ypar ^= 1;
     }
 
     // ---- fold the KS row-split copies and write this CTA's record ----
-    if (ROLE == 0) {
+    if (PASS == 2 && ROLE == 0) {
 #pragma unroll
         for (int b = 0; b < NB; b++) {
             gf[b] += __shfl_xor_sync(0xffffffffu, gf[b], 1);
             gf[b] += __shfl_xor_sync(0xffffffffu, gf[b], 2);
+            gj[b] += __shfl_xor_sync(0xffffffffu, gj[b], 1);
+            gj[b] += __shfl_xor_sync(0xffffffffu, gj[b], 2);
         }
         ff += __shfl_xor_sync(0xffffffffu, ff, 1);
         ff += __shfl_xor_sync(0xffffffffu, ff, 2);
@@ -279,12 +339,15 @@ __device__ __forceinline__ void consumer_loop(int64_t m, const double* __restric
             double* dst = rec + (size_t)(8 * bi + lr) * W + 8 * bj + 2 * lc;
             *reinterpret_cast<double2*>(dst) = make_double2(acc[q][0], acc[q][1]);
         }
-        if (ROLE == 0) {
+        if (PASS == 2 && ROLE == 0) {
             if (lc == 0) {
 #pragma unroll
-                for (int b = 0; b < NB; b++) rec[W * W + 8 * b + lr] = gf[b];
+                for (int b = 0; b < NB; b++) {
+                    rec[L::OFF_V1 + 8 * b + lr] = gf[b];
+                    rec[L::OFF_V2 + 8 * b + lr] = gj[b];
+                }
             }
-            if (lane == 0) rec[W * W + W] = ff;
+            if (lane == 0) rec[L::OFF_FF] = ff;
         }
         return;
     }
@@ -297,22 +360,25 @@ __device__ __forceinline__ void consumer_loop(int64_t m, const double* __restric
     for (int q = 0; q < NQ; q++)
         *reinterpret_cast<double2*>(red + (Q0 + q) * 64 + lane * 2) =
             make_double2(acc[q][0], acc[q][1]);
-    if (ROLE == 0) {
+    if (PASS == 2 && ROLE == 0) {
         if (lc == 0) {
 #pragma unroll
-            for (int b = 0; b < NB; b++) red[L::NBLK * 64 + 8 * b + lr] = gf[b];
+            for (int b = 0; b < NB; b++) {
+                red[L::NBLK * 64 + 8 * b + lr] = gf[b];
+                red[L::NBLK * 64 + W + 2 + 8 * b + lr] = gj[b];
+            }
         }
         if (lane == 0) red[L::NBLK * 64 + W] = ff;
     }
 }
 
 template <int NB, int PASS, bool EXACT, int... ROLES_>
-__device__ __forceinline__ void consumer_dispatch(int role, int64_t m, const double* rinvp_g,
+__device__ __forceinline__ void consumer_dispatch(int role, int64_t njobs, const double* rinvp_g,
                                                   int n, double* smem, uint64_t* full,
                                                   uint64_t* empty, double* rec,
                                                   std::integer_sequence<int, ROLES_...>) {
     ((role == ROLES_
-          ? (consumer_loop<NB, PASS, EXACT, ROLES_>(m, rinvp_g, n, smem, full, empty, rec), 0)
+          ? (consumer_loop<NB, PASS, EXACT, ROLES_>(njobs, rinvp_g, n, smem, full, empty, rec), 0)
           : 0),
      ...);
 }
@@ -320,10 +386,10 @@ __device__ __forceinline__ void consumer_dispatch(int role, int64_t m, const dou
 template <int NB, int PASS, bool EXACT>
 __global__ void __launch_bounds__(GramLayout<NB, PASS>::THREADS, 1)
 gram_kernel(int64_t m, int n, const double* __restrict__ J, const double* __restrict__ f,
-            const double* __restrict__ rinvp_g, double* __restrict__ partial) {
+            const double* __restrict__ rinvp_g, int sstride, double* __restrict__ partial) {
     typedef GramCfg<NB> C;
     typedef GramLayout<NB, PASS> L;
-    constexpr int T = C::T, S = C::S, CW = C::CW, W = L::W, QR = L::QR, QS = L::QS;
+    constexpr int T = C::T, S = L::S, CW = C::CW, W = L::W, QR = L::QR, QS = L::QS;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* smem = reinterpret_cast<double*>(smem_raw);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + L::MAIN_DOUBLES);
@@ -351,23 +417,27 @@ gram_kernel(int64_t m, int n, const double* __restrict__ J, const double* __rest
     __syncthreads();
 
     const int64_t ntiles = (m + T - 1) / T;
+    // jobs = tiles (pass 2, or pass 1 on every row) or sampled tiles (pass 1)
+    const int64_t njobs = (PASS == 1 && sstride > 1) ? ntiles / sstride : ntiles;
     if (warp == CW) {
         // ---------------- producer ----------------
         int stage = 0;
         uint32_t phase = 0;
         const uint32_t q_bytes = (uint32_t)(QR * n) * 8u;
-        for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        for (int64_t job = blockIdx.x; job < njobs; job += gridDim.x) {
             mbar_wait(&empty[stage], phase ^ 1);
+            const int64_t t = (PASS == 1) ? sample_tile(job, sstride) : job;
             const int64_t row0 = t * T;
             const int rows = (m - row0 < T) ? (int)(m - row0) : T;
             double* dj = smem + (size_t)stage * L::STAGE_DOUBLES;
             double* df = dj + 4 * QS;
             if (rows == T) {
-                if (lane == 0) mbar_expect_tx(&full[stage], 4u * q_bytes + T * 8u);
+                if (lane == 0)
+                    mbar_expect_tx(&full[stage], 4u * q_bytes + (PASS == 2 ? T * 8u : 0u));
                 __syncwarp();
                 if (lane < 4)
                     bulk_g2s(dj + lane * QS, J + (row0 + lane * QR) * n, q_bytes, &full[stage]);
-                else if (lane == 4)
+                else if (lane == 4 && PASS == 2)
                     bulk_g2s(df, f + row0, T * 8u, &full[stage]);
             } else {
                 // ragged last tile: plain loads, rows past m are zero
@@ -375,21 +445,22 @@ gram_kernel(int64_t m, int n, const double* __restrict__ J, const double* __rest
                     const int r = e / n, c = e % n;
                     dj[(r / QR) * QS + (r % QR) * RS + c] = (r < rows) ? J[(row0 + r) * n + c] : 0.0;
                 }
-                for (int r = lane; r < T; r += 32) df[r] = (r < rows) ? f[row0 + r] : 0.0;
+                if (PASS == 2)
+                    for (int r = lane; r < T; r += 32) df[r] = (r < rows) ? f[row0 + r] : 0.0;
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&full[stage]);
             }
             if (++stage == S) { stage = 0; phase ^= 1; }
         }
     } else {
-        consumer_dispatch<NB, PASS, EXACT>(warp % C::ROLES, m, rinvp_g, n, smem, full, empty, rec,
-                                           std::make_integer_sequence<int, C::ROLES>{});
+        consumer_dispatch<NB, PASS, EXACT>(warp % L::ROLES, njobs, rinvp_g, n, smem, full, empty, rec,
+                                           std::make_integer_sequence<int, L::ROLES>{});
     }
     if (L::KS > 1) {
         // fixed-order sum over the row-split copies
         __syncthreads();
         constexpr int PER = L::PER;
-        for (int e = threadIdx.x; e < PER - 1; e += L::THREADS) {
+        for (int e = threadIdx.x; e < PER; e += L::THREADS) {
             double s = 0.0;
 #pragma unroll
             for (int k = 0; k < L::KS; k++) s += smem[(size_t)k * PER + e];
@@ -400,19 +471,20 @@ gram_kernel(int64_t m, int n, const double* __restrict__ J, const double* __rest
                 const int bj = bi + qq;
                 rec[(size_t)(8 * bi + (ln >> 2)) * W + 8 * bj + 2 * (ln & 3) + c] = s;
             } else {
-                rec[W * W + (e - L::NBLK * 64)] = s;
+                rec[W * W + (e - L::NBLK * 64)] = s;       // Y^T f | f.f, pad | J^T f
             }
         }
     }
 }
 
-// out (n*n + n + 1 doubles): G (n x n row-major, upper triangle valid), g, f.f
-// = sum over the P per-CTA records, in CTA order.
+// out (blsq_tall_record_size(n) doubles): G (n x n row-major, upper triangle
+// valid) | Y^T f (n) | f.f | J^T f (n)  = sum over the P per-CTA records, in
+// CTA order.
 __global__ void gram_reduce_kernel(int P, int W, int REC, int n,
                                    const double* __restrict__ partial,
                                    double* __restrict__ out) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    const int total = n * n + n + 1;
+    const int total = n * n + 2 * n + 1;
     if (e >= total) return;
     int src;
     if (e < n * n) {
@@ -421,8 +493,10 @@ __global__ void gram_reduce_kernel(int P, int W, int REC, int n,
         src = r * W + c;
     } else if (e < n * n + n) {
         src = W * W + (e - n * n);
-    } else {
+    } else if (e == n * n + n) {
         src = W * W + W;
+    } else {
+        src = W * W + W + 2 + (e - n * n - n - 1);
     }
     double s = 0.0;
     for (int p = 0; p < P; p++) s += partial[(size_t)p * REC + src];
@@ -470,19 +544,21 @@ using blsq_tall::nb_for;
 
 template <int NB, int PASS, bool EXACT>
 int launch_gram_e(int64_t m, int n, const double* J, const double* f, const double* rinvp,
-                  double* work, double* out, cudaStream_t s) {
+                  int sstride, double* work, double* out, cudaStream_t s) {
     typedef GramLayout<NB, PASS> L;
     typedef GramCfg<NB> C;
     const int sms = sm_count();
-    const int64_t ntiles = (m + C::T - 1) / C::T;
+    int64_t ntiles = (m + C::T - 1) / C::T;
+    if (PASS == 1 && sstride > 1) ntiles /= sstride;
     int grid = (int)(ntiles < sms ? (ntiles > 0 ? ntiles : 1) : sms);
     cudaError_t e = cudaFuncSetAttribute(gram_kernel<NB, PASS, EXACT>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)L::SMEM_BYTES);
     if (e != cudaSuccess) return (int)e;
-    gram_kernel<NB, PASS, EXACT><<<grid, L::THREADS, L::SMEM_BYTES, s>>>(m, n, J, f, rinvp, work);
+    gram_kernel<NB, PASS, EXACT><<<grid, L::THREADS, L::SMEM_BYTES, s>>>(m, n, J, f, rinvp, sstride,
+                                                                         work);
     BLSQ_LAUNCH_CHECK();
-    const int total = n * n + n + 1;
+    const int total = n * n + 2 * n + 1;
     gram_reduce_kernel<<<(total + 255) / 256, 256, 0, s>>>(grid, L::W, L::REC, n, work, out);
     BLSQ_LAUNCH_CHECK();
     return 0;
@@ -490,9 +566,10 @@ int launch_gram_e(int64_t m, int n, const double* J, const double* f, const doub
 
 template <int NB, int PASS>
 int launch_gram(int64_t m, int n, const double* J, const double* f, const double* rinvp,
-                double* work, double* out, cudaStream_t s) {
-    if (n == 8 * NB) return launch_gram_e<NB, PASS, true>(m, n, J, f, rinvp, work, out, s);
-    return launch_gram_e<NB, PASS, false>(m, n, J, f, rinvp, work, out, s);
+                int sstride, double* work, double* out, cudaStream_t s) {
+    if (n == 8 * NB)
+        return launch_gram_e<NB, PASS, true>(m, n, J, f, rinvp, sstride, work, out, s);
+    return launch_gram_e<NB, PASS, false>(m, n, J, f, rinvp, sstride, work, out, s);
 }
 
 }  // namespace
@@ -502,22 +579,38 @@ extern "C" {
 int64_t blsq_tall_gram_work_size(int n) {
     if (n < 2 || n > 256) return BLSQ_E_UNSUPPORTED;
     const int W = 8 * nb_for(n);
-    return (int64_t)sm_count() * (W * W + W + 2);
+    return (int64_t)sm_count() * (W * W + 2 * W + 2);
+}
+
+int64_t blsq_tall_record_size(int n) {
+    if (n < 2 || n > 256) return BLSQ_E_UNSUPPORTED;
+    return ((int64_t)n * n + 2 * n + 1 + 1) & ~(int64_t)1;
+}
+
+/* pass 1 may run on one tile out of `stride`: keep >= 64 n^2 sampled rows so
+ * that cond(J R1^-1) stays close to 1 (entries of the sampled Gram deviate by
+ * ~1/sqrt(rows)); never sample small problems */
+int blsq_tall_sample_stride(int64_t m, int n) {
+    if (n < 2 || n > 256 || m < 0) return 1;
+    int64_t s = m / (64 * (int64_t)n * n);
+    return (int)(s < 1 ? 1 : (s > 8 ? 8 : s));
 }
 
 int blsq_tall_gram(int pass, int64_t m, int n, const double* J, const double* f,
-                   const double* Rinv, double* work, double* out, void* stream) {
-    if (m < 0 || !J || !f || !work || !out) return BLSQ_E_BADARG;
+                   const double* Rinv, int sstride, double* work, double* out, void* stream) {
+    if (m < 0 || !J || !work || !out) return BLSQ_E_BADARG;
     if (pass != 1 && pass != 2) return BLSQ_E_BADARG;
-    if (pass == 2 && !Rinv) return BLSQ_E_BADARG;
+    if (pass == 2 && (!Rinv || !f)) return BLSQ_E_BADARG;
+    if (pass == 2 || sstride < 1) sstride = 1;
+    if (!f) f = J;                                  /* pass 1 never reads f */
     // rows are moved by 16-byte-granular bulk copies
     if (n < 2 || n > 256 || (n & 1)) return BLSQ_E_UNSUPPORTED;
     if (((uintptr_t)J & 15) || ((uintptr_t)f & 15)) return BLSQ_E_BADARG;
     cudaStream_t s = (cudaStream_t)stream;
 #define BLSQ_GRAM_CASE(NB_)                                                         \
     case NB_:                                                                       \
-        return pass == 1 ? launch_gram<NB_, 1>(m, n, J, f, Rinv, work, out, s)      \
-                         : launch_gram<NB_, 2>(m, n, J, f, Rinv, work, out, s);
+        return pass == 1 ? launch_gram<NB_, 1>(m, n, J, f, Rinv, sstride, work, out, s) \
+                         : launch_gram<NB_, 2>(m, n, J, f, Rinv, sstride, work, out, s);
     switch (nb_for(n)) {
         BLSQ_GRAM_CASE(2)
         BLSQ_GRAM_CASE(4)

@@ -96,6 +96,7 @@ int blsq_tall_layout(int n, int64_t* out) {
     out[4] = TS_OBJ;  out[5] = TS_DELTA; out[6] = TS_GNORM; out[7] = L.ONB;
     out[8] = FL.SIZE; out[9] = FL.R;    out[10] = FL.QTF; out[11] = FL.G;
     out[12] = FL.OBJ; out[13] = FL.INFO; out[14] = FL.RINVP; out[15] = L.SCALE;
+    out[16] = FL.REFINE;
     return 0;
 }
 

@@ -77,3 +77,29 @@ def callbacks(model_name, jac_kind="exact", lib=None):
     if jac_kind != "exact":
         return fun, jac_kind
     return fun, jac
+
+
+def tall_callbacks(wl, lib=None):
+    """(fun, jac) for the tall workload ``synthetic.TallLinExp[Device]`` as two
+    fused kernels: the residual reads the design matrix from the first n-4
+    columns of the Jacobian buffer ``wl.J_t``; the Jacobian callback rewrites
+    the four exponential columns in place and returns the buffer."""
+    lib = lib or L.get_lib()
+    if not lib.has("blsq_model_linexp_fun"):
+        raise L.BlsqError("library built without blsq_models.cu")
+
+    def fun(x):
+        x = x.contiguous()
+        F = torch.empty(wl.m, dtype=torch.float64, device=x.device)
+        lib.call("blsq_model_linexp_fun", wl.m, wl.n, wl.J_t.data_ptr(),
+                 wl.t_t.data_ptr(), wl.y_t.data_ptr(), x.data_ptr(),
+                 F.data_ptr(), lib.stream(x))
+        return F
+
+    def jac(x):
+        x = x.contiguous()
+        lib.call("blsq_model_linexp_jac", wl.m, wl.n, wl.J_t.data_ptr(),
+                 wl.t_t.data_ptr(), x.data_ptr(), lib.stream(x))
+        return wl.J_t
+
+    return fun, jac

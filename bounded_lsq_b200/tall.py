@@ -136,7 +136,7 @@ def solve_tall(lib, method, fun, jac, x0, lb, ub, ftol, xtol, gtol, max_nfev,
     gwork = torch.empty(max(lay["gram_work"], 1), dtype=f64, device=dev)
     swork = torch.empty(4096, dtype=f64, device=dev)
     rwork = torch.empty(n * n, dtype=f64, device=dev)
-    GS = n * n + n + 1
+    GS = lay["record"]
     rec = torch.empty(GS, dtype=f64, device=dev)
     ssq = torch.empty(1, dtype=f64, device=dev)
     x_view = state[lay["x"]:lay["x"] + n]
@@ -167,20 +167,38 @@ def solve_tall(lib, method, fun, jac, x0, lb, ub, ftol, xtol, gtol, max_nfev,
                  new_lin, state.data_ptr(), istate.data_ptr(),
                  rwork.data_ptr(), st)
 
+    def gram(p, J, f, sstride):
+        launches[0] += 2                        # gram + reduce
+        t0 = tick()
+        lib.call("blsq_tall_gram", p, J.shape[0], n, J.data_ptr(), f.data_ptr(),
+                 fac[lay["rinvp"]:].data_ptr(), sstride, gwork.data_ptr(),
+                 rec.data_ptr(), st)
+        tock("gram%d" % p, t0)
+        return gather(rec)
+
+    def factor(p, recs):
+        launches[0] += 1
+        t0 = tick()
+        lib.call("blsq_tall_factor", p, n, nranks, GS,
+                 None if recs is None else recs.data_ptr(), fac.data_ptr(), st)
+        tock("factor", t0)
+
     def factorise(J, f):
-        m_loc = J.shape[0]
-        for p in (1, 2):
-            launches[0] += 3                    # gram + reduce + factor
-            t0 = tick()
-            lib.call("blsq_tall_gram", p, m_loc, n, J.data_ptr(), f.data_ptr(),
-                     fac[lay["rinvp"]:].data_ptr(), gwork.data_ptr(),
-                     rec.data_ptr(), st)
-            tock("gram%d" % p, t0)
-            t0 = tick()
-            recs = gather(rec)
-            lib.call("blsq_tall_factor", p, n, nranks, GS, recs.data_ptr(),
-                     fac.data_ptr(), st)
-            tock("factor", t0)
+        # preconditioner from a sample of the row tiles (all of them for
+        # small m: then this is CholeskyQR2), one exact pass, verified
+        sstride = int(lib._fn["blsq_tall_sample_stride"](J.shape[0], n))
+        if nranks > 1:
+            # every rank must take the same decision below
+            sstride = max(int(s) for s in gather(torch.tensor(
+                [float(sstride)], dtype=f64, device=dev)).view(-1).tolist())
+        factor(1, gram(1, J, f, sstride))
+        factor(2, gram(2, J, f, 1))
+        if sstride > 1:
+            for _ in range(2):
+                if float(fac[lay["refine"]].item()) == 0.0:     # host sync
+                    break
+                factor(3, None)
+                factor(2, gram(2, J, f, 1))
 
     round_(0, 1, 0)
     first = 1

@@ -154,22 +154,32 @@ int blsq_count_running(int64_t A, const int32_t* idx, const int32_t* istate,
 /* ---- tall mode: one problem, m_local rows on this rank, n even, n <= 256 --
  *
  * Per Jacobian evaluation (trf.py:244,264-274; dogbox.py:170,197-199) the
- * rank runs CholeskyQR2 on [J | f]:
- *   blsq_tall_gram(1)   -> record {J^T J, J^T f, f.f} of this rank's rows
+ * rank runs a preconditioned Cholesky QR on [J | f]:
+ *   blsq_tall_gram(1)   -> record {J_s^T J_s} over this rank's rows, or over
+ *                          one row tile out of `sstride` (sketch: pass 1 only
+ *                          has to deliver a preconditioner)
  *   (all-gather the records over the ranks)
- *   blsq_tall_factor(1) -> R1 = chol(sum of records), R1^-1, g, f.f
- *   blsq_tall_gram(2)   -> record {Y^T Y, Y^T f}, Y = J R1^-1
+ *   blsq_tall_factor(1) -> R1 = chol(sum of records), R1^-1
+ *   blsq_tall_gram(2)   -> record {Y^T Y, Y^T f, f.f, J^T f}, Y = J R1^-1,
+ *                          every row
  *   (all-gather)
- *   blsq_tall_factor(2) -> R = chol(.) R1 (J = Q R), Q^T f
- * A record is n*n + n + 1 doubles: G row-major (upper triangle valid), then
- * the n-vector, then f.f.  `fac` holds blsq_tall_fac_size(n) doubles:
- * R1 | R1^-1 | R | scratch (n*n each) | Q^T f (n) | g (n) | f.f | info.
- * info != 0: the Gram matrix was not numerically positive definite. */
+ *   blsq_tall_factor(2) -> R = chol(.) R1 (J = Q R), Q^T f, g = J^T f, f.f,
+ *                          and fac.refine = 1 when Y^T Y is too far from the
+ *                          identity for one Cholesky pass to be accurate; then
+ *   blsq_tall_factor(3) -> R1 <- R, R1^-1; repeat gram(2), factor(2)
+ * With sstride = 1 this is CholeskyQR2.  A record is
+ * blsq_tall_record_size(n) doubles: G row-major (upper triangle valid) |
+ * Y^T f (n) | f.f | J^T f (n).  `fac` holds blsq_tall_fac_size(n) doubles
+ * (offsets: blsq_tall_layout).  fac.info != 0: NaN/zero Jacobian.  Rank
+ * deficient Jacobians are handled by a diagonal shift of ~16 n eps |G|. */
 #define BLSQ_MAX_TALL_N 256
 int64_t blsq_tall_gram_work_size(int n);   /* doubles of `work` for blsq_tall_gram */
 int64_t blsq_tall_fac_size(int n);
+int64_t blsq_tall_record_size(int n);
+int blsq_tall_sample_stride(int64_t m_local, int n);   /* recommended sstride */
 int blsq_tall_gram(int pass, int64_t m, int n, const double* J, const double* f,
-                   const double* Rinv, double* work, double* out, void* stream);
+                   const double* Rinv, int sstride, double* work, double* out,
+                   void* stream);
 int blsq_tall_factor(int pass, int n, int nranks, int64_t gstride,
                      const double* grams, double* fac, void* stream);
 /* out[0] = sum f_i^2 over this rank's rows (trf.py:311, dogbox.py:224);
@@ -194,7 +204,8 @@ int blsq_tall_sumsq(int64_t m, const double* f, double* work, double* out,
  * work: n*n doubles (used when n > 128).  scaling: n doubles or null ('jac').
  * blsq_tall_layout: out[0..15] = state size, istate size, offsets of x,
  * x_new, obj, Delta, optimality, on_bound (istate), fac size, offsets of R,
- * Q^T f, g, f.f, info, packed R1^-1 inside fac, offset of scale. */
+ * Q^T f, g, f.f, info, packed R1^-1 inside fac, offset of scale (state),
+ * offset of refine (fac): 17 values. */
 int blsq_tall_layout(int n, int64_t* out_host);
 int blsq_tall_round(int method, int phase, int n, int64_t m_total, int nranks,
                     const double* ssq_parts, const double* fac,

@@ -26,6 +26,15 @@ int blsq_model_expdecay2(int64_t A, const int64_t* idx, int m, const double* t,
 int blsq_model_gausspeak(int64_t A, const int64_t* idx, int m, const double* t,
                          const double* X, const double* y, double* F,
                          void* stream);
+/* tall workload (C4/C5): J (m, n) keeps the constant design matrix in its
+ * first n-4 columns; x is a DEVICE pointer to n doubles.
+ *   fun: F = J[:, :n-4] x[:n-4] + x_k e^{-x_{k+1} t} + x_{k+2} e^{-x_{k+3} t} - y
+ *   jac: rewrites columns n-4..n-1 of J for the point x */
+int blsq_model_linexp_fun(int64_t m, int n, const double* J, const double* t,
+                          const double* y, const double* x, double* F,
+                          void* stream);
+int blsq_model_linexp_jac(int64_t m, int n, double* J, const double* t,
+                          const double* x, void* stream);
 #ifdef __cplusplus
 }
 #endif

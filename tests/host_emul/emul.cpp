@@ -348,8 +348,17 @@ extern "C" {
 int64_t blsq_tall_gram_work_size(int n) { return (n < 2 || n > 256) ? -2 : 8; }
 int64_t blsq_tall_fac_size(int n) { return (n < 2 || n > 256) ? -2 : FacLayout(n).SIZE; }
 
+int64_t blsq_tall_record_size(int n) {
+    return (n < 2 || n > 256) ? -2 : (((int64_t)n * n + 2 * n + 1 + 1) & ~(int64_t)1);
+}
+int blsq_tall_sample_stride(int64_t m, int n) {
+    if (n < 2 || n > 256 || m < 0) return 1;
+    int64_t s = m / (64 * (int64_t)n * n);
+    return (int)(s < 1 ? 1 : (s > 8 ? 8 : s));
+}
+
 int blsq_tall_gram(int pass, int64_t m, int n, const double* J, const double* f,
-                   const double* rinvp, double*, double* out, void*) {
+                   const double* rinvp, int sstride, double*, double* out, void*) {
     if (n < 2 || n > 256 || (n & 1)) return BLSQ_E_UNSUPPORTED;
     std::vector<double> X;
     if (pass == 2) {
@@ -366,9 +375,21 @@ int blsq_tall_gram(int pass, int64_t m, int n, const double* J, const double* f,
                     }
             }
     }
-    for (int e = 0; e < n * n + n + 1; e++) out[e] = 0.0;
+    for (int e = 0; e < n * n + 2 * n + 1; e++) out[e] = 0.0;
     std::vector<double> y(n);
-    for (int64_t r = 0; r < m; r++) {
+    // pass 1 may sample one 64-row tile out of sstride (same map as the kernel)
+    const int T = 64;
+    if (pass == 2 || sstride < 1) sstride = 1;
+    const int64_t ntiles = (m + T - 1) / T;
+    const int64_t njobs = (pass == 1 && sstride > 1) ? ntiles / sstride : ntiles;
+    for (int64_t job = 0; job < njobs; job++) {
+      int64_t t = job;
+      if (pass == 1 && sstride > 1) {
+          uint32_t h = (uint32_t)job * 2654435761u;
+          h ^= h >> 15;
+          t = job * sstride + (int64_t)(h % (uint32_t)sstride);
+      }
+      for (int64_t r = t * T; r < (t + 1) * T && r < m; r++) {
         const double* row = J + r * n;
         if (pass == 2) {
             for (int c = 0; c < n; c++) {
@@ -381,9 +402,13 @@ int blsq_tall_gram(int pass, int64_t m, int n, const double* J, const double* f,
         }
         for (int i = 0; i < n; i++) {
             for (int j = i; j < n; j++) out[i * n + j] = fma(y[i], y[j], out[i * n + j]);
-            out[n * n + i] = fma(y[i], f[r], out[n * n + i]);
+            if (pass == 2) {
+                out[n * n + i] = fma(y[i], f[r], out[n * n + i]);
+                out[n * n + n + 1 + i] = fma(row[i], f[r], out[n * n + n + 1 + i]);
+            }
         }
-        out[n * n + n] = fma(f[r], f[r], out[n * n + n]);
+        if (pass == 2) out[n * n + n] = fma(f[r], f[r], out[n * n + n]);
+      }
     }
     return 0;
 }
@@ -393,32 +418,7 @@ int blsq_tall_factor(int pass, int n, int nranks, int64_t gstride, const double*
     const FacLayout FL(n);
     const int n2 = n * n;
     std::vector<double> M(n2), diag0(n);
-    double shift = 0.0, dmax = 0.0;
-    int bad = 0;
-    for (int attempt = 0; attempt < 12; attempt++) {
-        for (int e = 0; e < n2 + n + 1; e++) {
-            double s = 0.0;
-            for (int r = 0; r < nranks; r++) s += grams[(size_t)r * gstride + e];
-            if (e < n2) {
-                if (e / n == e % n) { if (attempt == 0) diag0[e / n] = s; s += shift; }
-                M[e] = s;
-            } else if (attempt == 0) {
-                if (pass == 1) { if (e < n2 + n) fac[FL.G + e - n2] = s; else fac[FL.OBJ] = s; }
-                else if (e < n2 + n) fac[FL.QTF + e - n2] = s;
-            }
-        }
-        if (attempt == 0) for (int i = 0; i < n; i++) dmax = diag0[i] > dmax ? diag0[i] : dmax;
-        bad = host_chol_upper(M.data(), diag0.data(), n);
-        if (!bad) break;
-        if (!(dmax > 0.0)) break;
-        shift = (shift == 0.0) ? 16.0 * n * 2.220446049250313e-16 * dmax : shift * 10.0;
-    }
-    fac[FL.SHIFT + pass - 1] = shift;
-    if (bad) { fac[FL.INFO] = 1000.0 * pass + bad; return 0; }
-    if (pass == 1) {
-        for (int e = 0; e < n2; e++) fac[FL.R1 + e] = (e % n >= e / n) ? M[e] : 0.0;
-        std::vector<double> X(n2, 0.0);
-        host_inv_upper(M.data(), X.data(), n);
+    auto pack = [&](const std::vector<double>& X) {
         const int nb = FL.nb;
         for (int kb = 0; kb < nb; kb++)
             for (int jb = kb; jb < nb; jb++) {
@@ -430,6 +430,62 @@ int blsq_tall_factor(int pass, int n, int nranks, int64_t gstride, const double*
                             (r < n && c < n && c >= r) ? X[(size_t)r * n + c] : 0.0;
                     }
             }
+    };
+    if (pass == 3) {
+        for (int e = 0; e < n2; e++) { fac[FL.R1 + e] = fac[FL.R + e]; M[e] = fac[FL.R + e]; }
+        std::vector<double> X(n2, 0.0);
+        host_inv_upper(M.data(), X.data(), n);
+        pack(X);
+        fac[FL.REFINE] = 0.0;
+        fac[FL.INFO] = 0.0;
+        return 0;
+    }
+    double shift = 0.0, dmax = 0.0;
+    int bad = 0;
+    for (int attempt = 0; attempt < 12; attempt++) {
+        const int nvec = (pass == 2 && attempt == 0) ? 2 * n + 1 : 0;
+        for (int e = 0; e < n2 + nvec; e++) {
+            double s = 0.0;
+            for (int r = 0; r < nranks; r++) s += grams[(size_t)r * gstride + e];
+            if (e < n2) {
+                if (e / n == e % n) { if (attempt == 0) diag0[e / n] = s; s += shift; }
+                M[e] = s;
+            } else if (e < n2 + n) fac[FL.QTF + e - n2] = s;
+            else if (e == n2 + n) fac[FL.OBJ] = s;
+            else fac[FL.G + e - n2 - n - 1] = s;
+        }
+        if (attempt == 0) for (int i = 0; i < n; i++) dmax = diag0[i] > dmax ? diag0[i] : dmax;
+        if (attempt == 0 && pass == 2) {
+            bool far = false;
+            const double tiny = 1e-8 * dmax;
+            double dmin = dmax;
+            for (int i = 0; i < n; i++) {
+                if (!(diag0[i] > tiny)) continue;
+                double rs = 0.0;
+                for (int j = 0; j < n; j++) {
+                    if (j == i || !(diag0[j] > tiny)) continue;
+                    double gij = (j > i) ? M[i * n + j] : M[j * n + i];
+                    rs += fabs(gij) / sqrt(diag0[i] * diag0[j]);
+                }
+                if (!(rs <= 0.5)) far = true;
+                dmin = diag0[i] < dmin ? diag0[i] : dmin;
+            }
+            (void)dmin;
+            fac[FL.REFINE] = far ? 1.0 : 0.0;
+        }
+        bad = host_chol_upper(M.data(), diag0.data(), n);
+        if (!bad) break;
+        if (!(dmax > 0.0)) break;
+        shift = (shift == 0.0) ? 16.0 * n * 2.220446049250313e-16 * dmax : shift * 10.0;
+    }
+    fac[FL.SHIFT + pass - 1] = shift;
+    if (pass == 2 && shift != 0.0) fac[FL.REFINE] = 0.0;
+    if (bad) { fac[FL.INFO] = 1000.0 * pass + bad; return 0; }
+    if (pass == 1) {
+        for (int e = 0; e < n2; e++) fac[FL.R1 + e] = (e % n >= e / n) ? M[e] : 0.0;
+        std::vector<double> X(n2, 0.0);
+        host_inv_upper(M.data(), X.data(), n);
+        pack(X);
         fac[FL.INFO] = 0.0;
         return 0;
     }
@@ -465,6 +521,7 @@ int blsq_tall_layout(int n, int64_t* out) {
     out[4] = TS_OBJ;  out[5] = TS_DELTA; out[6] = TS_GNORM; out[7] = L.ONB;
     out[8] = FL.SIZE; out[9] = FL.R;    out[10] = FL.QTF; out[11] = FL.G;
     out[12] = FL.OBJ; out[13] = FL.INFO; out[14] = FL.RINVP; out[15] = L.SCALE;
+    out[16] = FL.REFINE;
     return 0;
 }
 

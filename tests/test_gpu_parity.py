@@ -164,3 +164,25 @@ def test_tall_large_properties(lib, dev):
     """m = 4M rows (no oracle at this size): the solve terminates feasible,
     and R^T R = J^T J, R^T (Q^T f) = J^T f hold to rounding for the factor."""
     cases.check_tall_large(lib, dev)
+
+
+def test_tall_fused_callbacks(lib, dev):
+    """The fused tall-model kernels (user-side, include/blsq_models.h) agree
+    with the torch callbacks, and a whole solve through them reproduces the
+    reference's result (golden case d)."""
+    from bounded_lsq_b200 import models, least_squares
+    from bounded_lsq_b200.synthetic import TallLinExp
+    wl = TallLinExp(20000, 64, seed=0, x0_tail=(0.8, 1.5, 0.3, 4.0)).to_device(dev)
+    fun, jac = models.tall_callbacks(wl)
+    x = cases.T(wl.x0 * 1.1, dev)
+    f_ref = wl.fun_t(x)
+    J_ref = wl.jac_t(x).clone()
+    assert float((fun(x) - f_ref).abs().max()) <= 1e-12 * float(f_ref.abs().max())
+    assert cases.bits(jac(x).cpu().numpy(), J_ref.cpu().numpy())
+    res = least_squares(fun, cases.T(wl.x0, dev), jac=jac,
+                        bounds=(cases.T(wl.lb, dev), cases.T(wl.ub, dev)), method="trf")
+    z = np.load(cases.os.path.join(cases.GOLDEN, "tall.npz"))
+    obj, status, nfev, njev = z["d_trf_scalars"][:4]
+    assert res.status == int(status) and res.nfev == int(nfev)
+    assert np.abs(res.x.cpu().numpy() - z["d_trf_x"]).max() < 1e-8 * np.abs(z["d_trf_x"]).max()
+    assert abs(res.obj_value - obj) < 1e-8 * obj

@@ -21,6 +21,9 @@ KEYS = [
     "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
     "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
     "sm__inst_executed_pipe_tensor.sum",
+    "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed",
+    "smsp__pipe_tensor_subpipe_dmma_cycles_active.avg",
+    "sm__cycles_elapsed.avg",
     "sm__warps_active.avg.pct_of_peak_sustained_active",
     "sm__maximum_warps_per_active_cycle_pct",
     "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
@@ -84,8 +87,10 @@ def full(path, out):
             fh.write(f"## {short(r[hdr.index('Kernel Name')])}  "
                      f"(id {r[0]})\n\n| metric | value | unit |\n|---|---|---|\n")
             for k in KEYS:
-                if k in hdr:
-                    i = hdr.index(k)
+                # some metrics carry a section prefix ("TPC.TriageCompute.<name>")
+                hits = [i for i, h in enumerate(hdr) if h == k or h.endswith("." + k)]
+                if hits:
+                    i = hits[0]
                     fh.write(f"| {k} | {r[i]} | {units[i]} |\n")
             fh.write("\n")
 
