@@ -56,3 +56,7 @@ def test_corpus_single(lib):
                                         ("d", "trf"), ("d", "dogbox")])
 def test_tall_golden(lib, tag, method):
     print(cases.check_tall_golden(lib, torch.device("cpu"), tag, method))
+
+
+def test_tall_options_vs_oracle(lib):
+    print(cases.check_tall_options_vs_oracle(lib, torch.device("cpu")))

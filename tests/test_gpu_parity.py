@@ -186,3 +186,9 @@ def test_tall_fused_callbacks(lib, dev):
     assert res.status == int(status) and res.nfev == int(nfev)
     assert np.abs(res.x.cpu().numpy() - z["d_trf_x"]).max() < 1e-8 * np.abs(z["d_trf_x"]).max()
     assert abs(res.obj_value - obj) < 1e-8 * obj
+
+
+def test_tall_options_vs_oracle(lib, dev):
+    """scaling='jac' / vector scaling / jac='2-point' in tall mode, oracle run
+    on the GPU box's host CPU."""
+    print(cases.check_tall_options_vs_oracle(lib, dev))
