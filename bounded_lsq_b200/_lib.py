@@ -32,6 +32,7 @@ SIGNATURES = {
     "blsq_in_bounds": [_l, _i, _p, _p, _p, _i, _p, _p],
     "blsq_find_intersection": [_l, _i, _p, _p, _p, _p, _i, _p, _p, _p, _p],
     "blsq_fd2_points": [_l, _p, _i, _p, _p, _p, _i, _d, _p, _p, _p],
+    "blsq_fd3_points": [_l, _p, _i, _p, _p, _p, _i, _d, _p, _p, _p],
     "blsq_init_batched": [_i, _l, _i, _p, _p, _p, _i, _p, _p, _p, _p],
     "blsq_linearise_batched": [_l, _p, _i, _i, _p, _p, _p, _p, _i, _p, _p, _p],
     "blsq_round_batched": [_i, _l, _p, _i, _i, _p, _p, _p, _p, _i, _p,

@@ -114,6 +114,8 @@ def solve_batched(lib, method, fun, jac, X0, lb, ub, ftol, xtol, gtol,
     if not jac_scaling:
         lib.check_tensor(scaling, f64, "scaling")
     fd = isinstance(jac, str)
+    fd3 = fd and jac == '3-point'
+    npts = 2 * n if fd3 else n                       # callback calls per FD Jacobian
     rel = float("nan") if diff_step is None else float(diff_step)
 
     state = torch.zeros((B, S), dtype=f64, device=dev)
@@ -125,8 +127,8 @@ def solve_batched(lib, method, fun, jac, X0, lb, ub, ftol, xtol, gtol,
     lin = torch.empty((B, LS), dtype=f64, device=dev)
     count = torch.zeros(1, dtype=torch.int32, device=dev)
     if fd:
-        Xp = torch.empty((n, B, n), dtype=f64, device=dev)
-        dx = torch.empty((B, n), dtype=f64, device=dev)
+        Xp = torch.empty((npts, B, n), dtype=f64, device=dev)
+        dx = torch.empty((B, 2 * n if fd3 else n), dtype=f64, device=dev)
     stream = lib.stream(X0)
     lib.call("blsq_init_batched", meth, B, n, X0.data_ptr(), lb.data_ptr(),
              ub.data_ptr(), bstride, state.data_ptr(), istate.data_ptr(),
@@ -188,22 +190,22 @@ def solve_batched(lib, method, fun, jac, X0, lb, ub, ftol, xtol, gtol,
                      lin.data_ptr(), stream)
             tock("linearise", t0, nrun)
         else:
-            Xpa = Xp.view(-1)[: n * A * n].view(n, A, n)
-            lib.call("blsq_fd2_points", A, ip, n, Xj.data_ptr(), lb.data_ptr(),
-                     ub.data_ptr(), bstride, rel, Xpa.data_ptr(),
-                     dx.data_ptr(), stream)
+            Xpa = Xp.view(-1)[: npts * A * n].view(npts, A, n)
+            lib.call("blsq_fd3_points" if fd3 else "blsq_fd2_points", A, ip, n,
+                     Xj.data_ptr(), lb.data_ptr(), ub.data_ptr(), bstride, rel,
+                     Xpa.data_ptr(), dx.data_ptr(), stream)
             launches += 1
             Fp = []
-            for i in range(n):
+            for i in range(npts):
                 Fi = _as_f64(fun(Xpa[i], idx), X0, "fun").contiguous()
                 if Fi.shape != F.shape:
                     raise RuntimeError("`fun` changed its output shape")
                 Fp.append(Fi)
-            plist = (C.c_void_p * n)(*[t.data_ptr() for t in Fp])
+            plist = (C.c_void_p * npts)(*[t.data_ptr() for t in Fp])
             tock("callbacks", t0, nrun)
             t0 = tick()
             lib.call("blsq_linearise_batched", A, ip, m, n, F.data_ptr(), None,
-                     C.cast(plist, C.c_void_p), dx.data_ptr(), 1,
+                     C.cast(plist, C.c_void_p), dx.data_ptr(), 2 if fd3 else 1,
                      istate.data_ptr(), lin.data_ptr(), stream)
             tock("linearise", t0, nrun)
         t0 = tick()

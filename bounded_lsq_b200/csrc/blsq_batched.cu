@@ -60,12 +60,14 @@ __device__ __forceinline__ double group_sum(double v) {
     return v;
 }
 
-template <int N> struct PtrList { const double* p[N]; };
+template <int N> struct PtrList { const double* p[2 * N]; };   // 2 per coordinate (3-point)
 
 // One group of G lanes (G = 8, 16 or 32) per problem; row (base + s*G + lane)
 // of the current chunk sits in a[s][*] of that lane.
-// MODE 0: analytic J (A, m, n).  MODE 1: finite differences, Fpert.p[i] is
-// F at the i-th perturbed batch, (A, m); dx is (A, n).
+// MODE 0: analytic J (A, m, n).  MODE 1: 2-point differences, Fpert.p[i] is
+// F at the i-th perturbed batch, (A, m); dx is (A, n).  MODE 2: 3-point
+// differences, Fpert.p[2i], p[2i+1] the two batches of coordinate i, dx is
+// (A, 2n): denominators, then the one-sided flags (blsq_fd3_points).
 template <int N, int G, int MODE>
 __global__ void __launch_bounds__(BLSQ_LIN_THREADS, BLSQ_LIN_MINB)
 lin_kernel(int64_t A, const int32_t* __restrict__ idx, int m,
@@ -89,10 +91,18 @@ lin_kernel(int64_t A, const int32_t* __restrict__ idx, int m,
     const double* Fp = F + slot * (int64_t)m;
     const double* Jp = (MODE == 0) ? J + slot * (int64_t)m * N : nullptr;
     double dxj[N];
+    bool onej[N];
     if (MODE == 1) {
 #pragma unroll
         for (int j = 0; j < N; j++)
             dxj[j] = valid ? 1.0 / dx[slot * N + j] : 1.0;   // reciprocal once
+    }
+    if (MODE == 2) {
+#pragma unroll
+        for (int j = 0; j < N; j++) {
+            dxj[j] = valid ? 1.0 / dx[slot * 2 * N + j] : 1.0;
+            onej[j] = valid ? dx[slot * 2 * N + N + j] != 0.0 : false;
+        }
     }
 
     double a[RPL + 1][C];        // a[RPL] = carried row of the running triangle
@@ -125,12 +135,23 @@ lin_kernel(int64_t A, const int32_t* __restrict__ idx, int m,
 #pragma unroll
                         for (int j = 0; j < N; j++) a[s][j] = __ldcs(rp + j);
                     }
-                } else {
+                } else if (MODE == 1) {
 #pragma unroll
                     for (int j = 0; j < N; j++)
                         a[s][j] = __ldcs(Fpert.p[j] + slot * (int64_t)m + row);
                 }
                 a[s][N] = __ldcs(Fp + row);
+                if (MODE == 2) {
+                    // scipy _dense_difference, '3-point': f2 - f1 (central) or
+                    // -3 f0 + 4 f1 - f2 (one sided), in NumPy's evaluation order
+                    const double f0 = a[s][N];
+#pragma unroll
+                    for (int j = 0; j < N; j++) {
+                        const double f1 = __ldcs(Fpert.p[2 * j] + slot * (int64_t)m + row);
+                        const double f2 = __ldcs(Fpert.p[2 * j + 1] + slot * (int64_t)m + row);
+                        a[s][j] = onej[j] ? ((-3.0 * f0 + 4 * f1) - f2) : (f2 - f1);
+                    }
+                }
             } else {
 #pragma unroll
                 for (int j = 0; j < C; j++) a[s][j] = 0.0;
@@ -146,6 +167,13 @@ lin_kernel(int64_t A, const int32_t* __restrict__ idx, int m,
 #pragma unroll
                 for (int j = 0; j < N; j++)
                     a[s][j] = (a[s][j] - a[s][N]) * dxj[j];
+            }
+        }
+        if (MODE == 2) {
+#pragma unroll
+            for (int s = 0; s < RPL; s++) {
+#pragma unroll
+                for (int j = 0; j < N; j++) a[s][j] *= dxj[j];
             }
         }
         // ---- g = J^T f and f.f on the raw rows (trf.py:244, 229) ----
@@ -359,8 +387,11 @@ int launch_lin_g(int64_t A, const int32_t* idx, int m, const double* F,
     if (jac_mode == 0)
         lin_kernel<N, G, 0><<<(unsigned)blocks, BLSQ_LIN_THREADS, 0, s>>>(
             A, idx, m, F, J, pl, dx, istate, lin);
-    else
+    else if (jac_mode == 1)
         lin_kernel<N, G, 1><<<(unsigned)blocks, BLSQ_LIN_THREADS, 0, s>>>(
+            A, idx, m, F, J, pl, dx, istate, lin);
+    else
+        lin_kernel<N, G, 2><<<(unsigned)blocks, BLSQ_LIN_THREADS, 0, s>>>(
             A, idx, m, F, J, pl, dx, istate, lin);
     BLSQ_LAUNCH_CHECK();
     return 0;
@@ -373,7 +404,8 @@ int launch_lin(int64_t A, const int32_t* idx, int m, const double* F,
                cudaStream_t s) {
     constexpr int RPL = LinCfg<N>::RPL;
     PtrList<N> pl;
-    for (int j = 0; j < N; j++) pl.p[j] = (jac_mode == 1) ? Fp_host[j] : nullptr;
+    const int np = jac_mode == 2 ? 2 * N : (jac_mode == 1 ? N : 0);
+    for (int j = 0; j < 2 * N; j++) pl.p[j] = (j < np) ? Fp_host[j] : nullptr;
     // smallest lane group whose registers hold all m rows (else 32 + chunks)
     if (m <= 8 * RPL)
         return launch_lin_g<N, 8>(A, idx, m, F, J, pl, dx, jac_mode, istate, lin, s);
@@ -473,11 +505,11 @@ int blsq_linearise_batched(int64_t A, const int32_t* idx, int m, int n,
                            int jac_mode, const int32_t* istate, double* lin,
                            void* stream) {
     if (A < 0 || m < 1 || !F || !istate || !lin) return BLSQ_E_BADARG;
-    if (jac_mode != 0 && jac_mode != 1) return BLSQ_E_BADARG;
+    if (jac_mode < 0 || jac_mode > 2) return BLSQ_E_BADARG;
     if (jac_mode == 0 && !J) return BLSQ_E_BADARG;
-    if (jac_mode == 1 && (!dx || !Fp_host)) return BLSQ_E_BADARG;
-    if (jac_mode == 1)
-        for (int j = 0; j < n && j < BLSQ_MAX_BATCHED_N; j++)
+    if (jac_mode != 0 && (!dx || !Fp_host)) return BLSQ_E_BADARG;
+    if (jac_mode != 0 && n >= 1 && n <= BLSQ_MAX_BATCHED_N)
+        for (int j = 0; j < jac_mode * n; j++)
             if (!Fp_host[j]) return BLSQ_E_BADARG;
     if (A == 0) return 0;
     BLSQ_DISPATCH_N(n, {

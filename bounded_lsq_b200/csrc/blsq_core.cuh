@@ -1121,4 +1121,32 @@ BLSQ_HD double fd2_step(double x, double lb, double ub, double rel_step) {
     return out;
 }
 
+// 3-point scheme (scipy _compute_absolute_step + _adjust_scheme_to_bounds with
+// '2-sided', num_steps = 1): central difference where both x - h and x + h fit,
+// else a one-sided 3-point stencil x + h, x + 2h (h possibly negative and
+// shrunk to half the room), else central again with h = the smaller distance.
+BLSQ_HD double fd3_step(double x, double lb, double ub, double rel_step, bool& one_sided) {
+    const double CBRT_EPS = 0x1.965fea53d6e41p-18;       // EPS ** (1 / 3), 6.055454452393343e-06
+    double sgn = (x >= 0) ? 1.0 : -1.0;
+    double h_def = CBRT_EPS * sgn * np_max(1.0, fabs(x));
+    double h = h_def;
+    if (rel_step == rel_step) {
+        h = rel_step * sgn * fabs(x);
+        double dx = (x + h) - x;
+        if (dx == 0) h = h_def;
+    }
+    h = fabs(h);
+    double below = x - lb, above = ub - x;
+    bool central = (below >= h) && (above >= h);
+    double out = h;
+    one_sided = false;
+    if (!central) {
+        if (above >= below) { out = np_min(h, 0.5 * above); one_sided = true; }
+        else { out = -np_min(h, 0.5 * below); one_sided = true; }
+        double min_dist = np_min(above, below);
+        if (fabs(out) <= min_dist) { out = min_dist; one_sided = false; }
+    }
+    return out;
+}
+
 }  // namespace blsq

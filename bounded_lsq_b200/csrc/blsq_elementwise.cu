@@ -187,6 +187,42 @@ __global__ void fd2_points_kernel(int64_t A, const int32_t* __restrict__ idx,
     Xp[t] = xk;
 }
 
+// 3-point scheme: batches 2i and 2i+1 are the two evaluation points of
+// coordinate i -- (x - h, x + h) central, (x + h, x + 2h) one sided;
+// dxo[slot, i] = the denominator, dxo[slot, n + i] = 1.0 when one sided
+__global__ void fd3_points_kernel(int64_t A, const int32_t* __restrict__ idx,
+                                  int n, const double* __restrict__ x,
+                                  const double* __restrict__ lb,
+                                  const double* __restrict__ ub, int bstride,
+                                  double rel_step, double* __restrict__ Xp,
+                                  double* __restrict__ dxo) {
+    int64_t t = gtid();
+    int64_t total = A * n * n;
+    if (t >= total) return;
+    int k = (int)(t % n);
+    int64_t slot = (t / n) % A;
+    int i = (int)(t / ((int64_t)n * A));
+    double xk = x[slot * n + k];
+    double x1 = xk, x2 = xk;
+    if (k == i) {
+        int64_t pid = idx ? idx[slot] : slot;
+        bool one;
+        double h = fd3_step(xk, lb[pid * bstride + k], ub[pid * bstride + k], rel_step, one);
+        if (one) {
+            x1 = xk + h;
+            x2 = xk + 2 * h;
+            dxo[slot * 2 * n + i] = x2 - xk;
+        } else {
+            x1 = xk - h;
+            x2 = xk + h;
+            dxo[slot * 2 * n + i] = x2 - x1;
+        }
+        dxo[slot * 2 * n + n + i] = one ? 1.0 : 0.0;
+    }
+    Xp[((int64_t)(2 * i) * A + slot) * n + k] = x1;
+    Xp[((int64_t)(2 * i + 1) * A + slot) * n + k] = x2;
+}
+
 }  // namespace
 
 extern "C" {
@@ -289,6 +325,18 @@ int blsq_fd2_points(int64_t A, const int32_t* idx, int n, const double* x,
     int64_t total = A * n * n;
     fd2_points_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         A, idx, n, x, lb, ub, bstride, rel_step, Xp, dx);
+    BLSQ_LAUNCH_CHECK();
+    return 0;
+}
+
+int blsq_fd3_points(int64_t A, const int32_t* idx, int n, const double* x,
+                    const double* lb, const double* ub, int bstride,
+                    double rel_step, double* Xp, double* dxo, void* stream) {
+    if (!x || !lb || !ub || !Xp || !dxo) return BLSQ_E_BADARG;
+    BLSQ_CHECK_COMMON(A, n, bstride)
+    int64_t total = A * n * n;
+    fd3_points_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        A, idx, n, x, lb, ub, bstride, rel_step, Xp, dxo);
     BLSQ_LAUNCH_CHECK();
     return 0;
 }

@@ -123,10 +123,6 @@ def _validate_common(method, bounds, jac):
         raise ValueError("`bounds` must contain 2 elements.")
     if jac not in ('2-point', '3-point') and not callable(jac):
         raise ValueError("`jac` must be '2-point', '3-point' or callable.")
-    if jac == '3-point':
-        raise NotImplementedError(
-            "jac='3-point' is not built yet (SURVEY 8f rank 1); use "
-            "'2-point' or a callable")
 
 
 def least_squares_batched(fun, x0, jac='2-point', bounds=(-float('inf'), float('inf')),
@@ -259,22 +255,37 @@ def least_squares(fun, x0, jac='2-point', bounds=(-float('inf'), float('inf')),
     if callable(jac):
         res.jac = jac_b(x.reshape(1, n))[0]
     else:
-        res.jac = fd_jacobian(lib, fun_b, x, res.fun, lb, ub, diff_step)
+        res.jac = fd_jacobian(lib, fun_b, x, res.fun, lb, ub, diff_step, jac)
     res.message = TERMINATION_MESSAGES[res.status]
     res.success = res.status > 0
     return res
 
 
-def fd_jacobian(lib, fun_b, x, f0, lb, ub, diff_step=None):
-    """Dense 2-point Jacobian (m, n) at one point, through blsq_fd2_points."""
+def fd_jacobian(lib, fun_b, x, f0, lb, ub, diff_step=None, method='2-point'):
+    """Dense finite-difference Jacobian (m, n) at one point through
+    blsq_fd2_points / blsq_fd3_points (scipy _dense_difference)."""
     n = x.shape[0]
-    Xp = torch.empty((n, 1, n), dtype=torch.float64, device=x.device)
-    dx = torch.empty((1, n), dtype=torch.float64, device=x.device)
+    f64 = torch.float64
     rel = float("nan") if diff_step is None else float(diff_step)
-    lib.call("blsq_fd2_points", 1, None, n, x.contiguous().data_ptr(),
-             lb.data_ptr(), ub.data_ptr(), 0, rel, Xp.data_ptr(),
-             dx.data_ptr(), lib.stream(x))
-    cols = [(fun_b(Xp[i])[0] - f0) / dx[0, i] for i in range(n)]
+    xc = x.contiguous()
+    if method == '2-point':
+        Xp = torch.empty((n, 1, n), dtype=f64, device=x.device)
+        dx = torch.empty((1, n), dtype=f64, device=x.device)
+        lib.call("blsq_fd2_points", 1, None, n, xc.data_ptr(), lb.data_ptr(),
+                 ub.data_ptr(), 0, rel, Xp.data_ptr(), dx.data_ptr(),
+                 lib.stream(x))
+        cols = [(fun_b(Xp[i])[0] - f0) / dx[0, i] for i in range(n)]
+        return torch.stack(cols, dim=1)
+    Xp = torch.empty((2 * n, 1, n), dtype=f64, device=x.device)
+    dxo = torch.empty((1, 2 * n), dtype=f64, device=x.device)
+    lib.call("blsq_fd3_points", 1, None, n, xc.data_ptr(), lb.data_ptr(),
+             ub.data_ptr(), 0, rel, Xp.data_ptr(), dxo.data_ptr(), lib.stream(x))
+    one = dxo[0, n:].tolist()
+    cols = []
+    for i in range(n):
+        f1, f2 = fun_b(Xp[2 * i])[0], fun_b(Xp[2 * i + 1])[0]
+        df = (-3.0 * f0 + 4 * f1 - f2) if one[i] else (f2 - f1)
+        cols.append(df / dxo[0, i])
     return torch.stack(cols, dim=1)
 
 

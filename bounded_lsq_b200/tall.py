@@ -57,21 +57,32 @@ class _Gather:
         return int(t.item())
 
 
-def _fd_jacobian_tall(lib, fun, x, f0, lb, ub, diff_step, st):
-    """2-point Jacobian of this rank's rows (least_squares.py:357-365):
-    n extra ``fun`` calls, J[:, i] = (f(x + h_i e_i) - f0) / dx_i with scipy's
-    bound-aware h (blsq_fd2_points, bit exact)."""
+def _fd_jacobian_tall(lib, fun, x, f0, lb, ub, diff_step, st, method='2-point'):
+    """Finite-difference Jacobian of this rank's rows (least_squares.py:
+    357-365): n ('2-point') or 2n ('3-point') extra ``fun`` calls at scipy's
+    bound-aware points (blsq_fd2_points / blsq_fd3_points, bit exact)."""
     n = x.shape[0]
     f64 = torch.float64
-    Xp = torch.empty((n, 1, n), dtype=f64, device=x.device)
-    dx = torch.empty((1, n), dtype=f64, device=x.device)
     rel = float("nan") if diff_step is None else float(diff_step)
-    lib.call("blsq_fd2_points", 1, None, n, x.contiguous().data_ptr(),
-             lb.data_ptr(), ub.data_ptr(), 0, rel, Xp.data_ptr(),
-             dx.data_ptr(), st)
     J = torch.empty((f0.shape[0], n), dtype=f64, device=x.device)
+    xc = x.contiguous()
+    if method == '2-point':
+        Xp = torch.empty((n, 1, n), dtype=f64, device=x.device)
+        dx = torch.empty((1, n), dtype=f64, device=x.device)
+        lib.call("blsq_fd2_points", 1, None, n, xc.data_ptr(), lb.data_ptr(),
+                 ub.data_ptr(), 0, rel, Xp.data_ptr(), dx.data_ptr(), st)
+        for i in range(n):
+            J[:, i] = (fun(Xp[i, 0]) - f0) / dx[0, i]
+        return J
+    Xp = torch.empty((2 * n, 1, n), dtype=f64, device=x.device)
+    dxo = torch.empty((1, 2 * n), dtype=f64, device=x.device)
+    lib.call("blsq_fd3_points", 1, None, n, xc.data_ptr(), lb.data_ptr(),
+             ub.data_ptr(), 0, rel, Xp.data_ptr(), dxo.data_ptr(), st)
+    one = dxo[0, n:].tolist()                            # host sync (n flags)
     for i in range(n):
-        J[:, i] = (fun(Xp[i, 0]) - f0) / dx[0, i]
+        f1, f2 = fun(Xp[2 * i, 0]), fun(Xp[2 * i + 1, 0])
+        df = (-3.0 * f0 + 4 * f1 - f2) if one[i] else (f2 - f1)
+        J[:, i] = df / dxo[0, i]
     return J
 
 
@@ -127,7 +138,7 @@ def solve_tall(lib, method, fun, jac, x0, lb, ub, ftol, xtol, gtol, max_nfev,
                 J = J.unsqueeze(0)
             J = J.to(f64)
         else:
-            J = _fd_jacobian_tall(lib, call_fun, x, f, lb, ub, diff_step, st)
+            J = _fd_jacobian_tall(lib, call_fun, x, f, lb, ub, diff_step, st, jac)
         return J if J.is_contiguous() else J.contiguous()
 
     state = torch.zeros(lay["state_size"], dtype=f64, device=dev)

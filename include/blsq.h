@@ -98,6 +98,15 @@ int blsq_fd2_points(int64_t A, const int32_t* idx, int n, const double* x,
                     const double* lb, const double* ub, int bstride,
                     double rel_step, double* Xp, double* dx, void* stream);
 
+/* 3-point scheme (jac='3-point', scipy '2-sided' with the one-sided fallback
+ * near a bound).  Xp has layout (2n, A, n): batches 2i, 2i+1 are the two
+ * evaluation points of coordinate i -- (x - h, x + h) for a central
+ * difference, (x + h, x + 2h) for the one-sided 3-point stencil.  dxo is
+ * (A, 2n): dxo[s, i] = the denominator, dxo[s, n + i] = 1.0 if one sided. */
+int blsq_fd3_points(int64_t A, const int32_t* idx, int n, const double* x,
+                    const double* lb, const double* ub, int bstride,
+                    double rel_step, double* Xp, double* dxo, void* stream);
+
 /* ---- batched solve: init -> [callbacks -> linearise -> round]* -------- */
 
 /* trf.py:201 (x = make_strictly_feasible(x0, rstep=1e-10)) / dogbox.py:131
@@ -116,6 +125,9 @@ int blsq_init_batched(int method, int64_t B, int n, const double* x0,
  *               blsq_fd2_points, dx (A, n) its denominators;
  *               J[:, i] = (Fp_i - f) / dx_i is formed in registers (scipy
  *               _dense_difference) and never materialised.
+ *   jac_mode 2: 3-point: Fp_host holds 2n device pointers in the batch order
+ *               of blsq_fd3_points, dx is its (A, 2n) dxo array;
+ *               J[:, i] = (f2 - f1) / dx_i or (-3 f + 4 f1 - f2) / dx_i.
  * Slots whose problem is no longer running are skipped. */
 int blsq_linearise_batched(int64_t A, const int32_t* idx, int m, int n,
                            const double* F, const double* J,

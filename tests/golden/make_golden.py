@@ -450,6 +450,13 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "tall":
         gen_tall()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "fd3":
+        # jac='3-point' on the C3 model, both methods
+        gen_batched("c3_trf_3point.npz", GaussPeak(128), "trf", "3-point",
+                    48, seed=2)
+        gen_batched("c3_dogbox_3point.npz", GaussPeak(128), "dogbox",
+                    "3-point", 48, seed=3)
+        sys.exit(0)
     rng = np.random.default_rng(20261018)
     gen_helpers(rng)
     gen_tr_subproblem(rng)
@@ -461,4 +468,8 @@ if __name__ == "__main__":
                 seed=1)
     gen_batched("c3_trf_2point.npz", GaussPeak(128), "trf", "2-point", 64,
                 seed=1)
+    gen_batched("c3_trf_3point.npz", GaussPeak(128), "trf", "3-point", 48,
+                seed=2)
+    gen_batched("c3_dogbox_3point.npz", GaussPeak(128), "dogbox", "3-point",
+                48, seed=3)
     gen_tall()

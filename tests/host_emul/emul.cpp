@@ -41,7 +41,13 @@ static void lin_host(int m, const double* F, const double* J,
         double f0 = F[slot * m + r];
         for (int j = 0; j < N; j++) {
             if (mode == 0) a[r * C + j] = J[(slot * m + r) * N + j];
-            else a[r * C + j] = (Fp[j][slot * m + r] - f0) / dx[slot * N + j];
+            else if (mode == 1) a[r * C + j] = (Fp[j][slot * m + r] - f0) / dx[slot * N + j];
+            else {
+                const double f1 = Fp[2 * j][slot * m + r], f2 = Fp[2 * j + 1][slot * m + r];
+                const bool one = dx[slot * 2 * N + N + j] != 0.0;
+                const double df = one ? ((-3.0 * f0 + 4 * f1) - f2) : (f2 - f1);
+                a[r * C + j] = df / dx[slot * 2 * N + j];
+            }
         }
         a[r * C + N] = f0;
     }
@@ -196,6 +202,28 @@ int blsq_fd2_points(int64_t A, const int32_t* idx, int n, const double* x,
                     xk = xp;
                 }
                 Xp[((int64_t)i * A + s) * n + k] = xk;
+            }
+        }
+    return 0;
+}
+
+int blsq_fd3_points(int64_t A, const int32_t* idx, int n, const double* x,
+                    const double* lb, const double* ub, int bs, double rel,
+                    double* Xp, double* dxo, void*) {
+    for (int i = 0; i < n; i++)
+        for (int64_t s = 0; s < A; s++) {
+            int64_t pid = idx ? idx[s] : s;
+            for (int k = 0; k < n; k++) {
+                double xk = x[s * n + k], x1 = xk, x2 = xk;
+                if (k == i) {
+                    bool one;
+                    double h = fd3_step(xk, lb[pid * bs + k], ub[pid * bs + k], rel, one);
+                    if (one) { x1 = xk + h; x2 = xk + 2 * h; dxo[s * 2 * n + i] = x2 - xk; }
+                    else { x1 = xk - h; x2 = xk + h; dxo[s * 2 * n + i] = x2 - x1; }
+                    dxo[s * 2 * n + n + i] = one ? 1.0 : 0.0;
+                }
+                Xp[((int64_t)(2 * i) * A + s) * n + k] = x1;
+                Xp[((int64_t)(2 * i + 1) * A + s) * n + k] = x2;
             }
         }
     return 0;

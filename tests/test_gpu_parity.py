@@ -35,7 +35,8 @@ def test_golden_exact_jac(lib, dev, name):
     print(name, s)
 
 
-@pytest.mark.parametrize("name", ["c3_dogbox_2point", "c3_trf_2point"])
+@pytest.mark.parametrize("name", ["c3_dogbox_2point", "c3_trf_2point",
+                                  "c3_trf_3point", "c3_dogbox_3point"])
 def test_golden_fd_jac(lib, dev, name):
     s = cases.check_golden_fd_jac(lib, dev, name)
     print(name, s)
