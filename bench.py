@@ -457,6 +457,10 @@ def main():
                     help="residual/Jacobian callbacks: the fused CUDA model "
                          "op shipped for the synthetic workloads, or plain "
                          "torch elementwise ops")
+    ap.add_argument("--rounds-log", default=None,
+                    help="write the per-round CUDA-event timings of the "
+                         "instrumented step (running problems, callbacks / "
+                         "linearise / round ms) to this CSV file")
     ap.add_argument("--rows", type=int, default=None,
                     help="tall workload: total rows (default 2^24)")
     args = ap.parse_args()
@@ -572,6 +576,13 @@ def main():
     solve(y_dev, x0_dev, collect)
     torch.cuda.synchronize()
     ksum = drv.summarize_timers(collect)
+    if args.rounds_log and rank == 0:
+        with open(args.rounds_log, "w") as fh:
+            fh.write("round,running,callbacks_ms,linearise_ms,round_ms\n")
+            cols = [collect.get(k, []) for k in ("callbacks", "linearise", "round")]
+            for i, evs in enumerate(zip(*cols)):
+                ms = [a.elapsed_time(b) for a, b, _ in evs]
+                fh.write("%d,%d,%.5f,%.5f,%.5f\n" % (i, evs[0][2], *ms))
 
     # ---- end to end: host buffers in, host results out -------------------
     barrier()
@@ -609,7 +620,8 @@ def main():
 
     peaks = {}
     try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            peaks = json.load(fh)
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))

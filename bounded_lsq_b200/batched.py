@@ -19,6 +19,9 @@ compacts the active set (``idx``) so the callbacks only see running problems.
 from __future__ import annotations
 
 import ctypes as C
+import os
+import sys
+import warnings
 
 import torch
 
@@ -54,6 +57,7 @@ class BatchedCallbacks:
         self.fun, self.jac = fun, jac
         self.args, self.kwargs = tuple(args), dict(kwargs or {})
         self.B = B
+        self._gathered = (None, None)     # (idx, gathered args) of the last call
 
     def _call(self, fn, X, idx):
         if getattr(fn, "blsq_indexed", False):
@@ -63,7 +67,11 @@ class BatchedCallbacks:
             k = {n: (v.tensor if isinstance(v, PerProblem) else v)
                  for n, v in self.kwargs.items()}
             return fn(X, idx, *a, **k)
-        a, k = _gather_args(self.args, self.kwargs, idx)
+        # the active set only changes when the driver compacts it: gather the
+        # per-problem data once per compaction, not once per callback
+        if self._gathered[0] is not idx or idx is None:
+            self._gathered = (idx, _gather_args(self.args, self.kwargs, idx))
+        a, k = self._gathered[1]
         return fn(X, *a, **k)
 
     def f(self, X, idx):
@@ -71,6 +79,41 @@ class BatchedCallbacks:
 
     def j(self, X, idx):
         return self._call(self.jac, X, idx)
+
+
+_SIDE = {}
+
+
+def _side_stream(dev):
+    s = _SIDE.get(dev)
+    if s is None:
+        s = _SIDE[dev] = torch.cuda.Stream(dev)
+    return s
+
+
+_POOL = {}
+
+
+def _graph_pool(dev):
+    """One private allocator pool per device shared by all tail graphs: its
+    segments are reused by the next capture instead of going back to
+    cudaMalloc / cudaFree."""
+    p = _POOL.get(dev)
+    if p is None:
+        p = _POOL[dev] = torch.cuda.graph_pool_handle()
+    return p
+
+
+# callbacks whose capture failed once are not tried again (a failed capture
+# costs a device synchronisation and an allocator flush)
+_NOT_CAPTURABLE = set()
+
+
+def _cb_key(fun, jac):
+    def k(f):
+        f = getattr(f, "__self__", f)             # BatchedCallbacks.f / .j
+        return (id(getattr(f, "fun", f)), id(getattr(f, "jac", None)))
+    return (k(fun), jac if isinstance(jac, str) else k(jac))
 
 
 def _as_f64(t, like, what):
@@ -86,7 +129,7 @@ def _as_f64(t, like, what):
 def solve_batched(lib, method, fun, jac, X0, lb, ub, ftol, xtol, gtol,
                   max_nfev, scaling, diff_step=None, check_every=1,
                   compact_below=0.75, tail_below=8192, trace=None,
-                  timers=None):
+                  timers=None, graph_tail_rounds=None):
     """Run ``method`` ('trf' | 'dogbox') on B problems.
 
     fun(X, idx) -> (A, m); jac is a callable jac(X, idx) -> (A, m, n) or the
@@ -159,7 +202,11 @@ def solve_batched(lib, method, fun, jac, X0, lb, ub, ftol, xtol, gtol,
     m = None
     rounds = 0
     launches = 0
-    while A > 0:
+
+    def one_round(A, idx, idx32, first, nrun):
+        """Callbacks + linearise + round for the A compacted slots."""
+        nonlocal m, launches
+        stream = lib.stream(X0)            # the capture stream inside a graph
         Xa = Xnew[:A]
         Xj = Xa if (Xjac is None or first) else Xjac[:A]
         t0 = tick()
@@ -218,6 +265,87 @@ def solve_batched(lib, method, fun, jac, X0, lb, ub, ftol, xtol, gtol,
         if timers is not None:
             timers["shape"] = (n, m, LS, S)
         launches += 2
+
+    def count_running(A, idx32):
+        nonlocal launches
+        lib.call("blsq_count_running", A,
+                 None if idx32 is None else idx32.data_ptr(),
+                 istate.data_ptr(), count.data_ptr(), lib.stream(X0))
+        launches += 1
+
+    def graph_tail(A, idx, idx32, nrun):
+        """The latency-sized tail of the batch (A <= tail_below slots, often a
+        hundred more rounds for the slowest problems): GRAPH_ROUNDS rounds +
+        the status count are captured ONCE into a CUDA graph and replayed, so
+        a tail round costs the GPU a few microseconds instead of the host's
+        launch path.  Finished problems are skipped inside the kernels, extra
+        rounds after the last one finishes are no-ops.  Returns the rounds
+        run, or None if the callbacks cannot be captured (host syncs,
+        data-dependent shapes): the caller then carries on eagerly."""
+        nonlocal launches
+        one_round(A, idx, idx32, 0, nrun)       # eager: errors surface here
+        r = 1
+        l1 = launches
+        # torch.cuda.graph() synchronises the device and flushes the caching
+        # allocator on entry (every later allocation of the batch would go
+        # back to cudaMalloc); capture_begin / capture_end on a side stream
+        # do neither.
+        dbg = os.environ.get("BLSQ_GRAPH_DEBUG")
+        if dbg:
+            import time
+            torch.cuda.synchronize(dev)
+            tt = [time.perf_counter()]
+        g = torch.cuda.CUDAGraph()
+        cur = torch.cuda.current_stream(dev)
+        side = _side_stream(dev)
+        side.wait_stream(cur)
+        try:
+            with torch.cuda.stream(side):
+                g.capture_begin(pool=_graph_pool(dev))
+                if dbg:
+                    tt.append(time.perf_counter())
+                try:
+                    for _ in range(GRAPH_ROUNDS):
+                        one_round(A, idx, idx32, 0, nrun)
+                    count_running(A, idx32)
+                finally:
+                    if dbg:
+                        tt.append(time.perf_counter())
+                    g.capture_end()
+            cur.wait_stream(side)
+            if dbg:
+                tt.append(time.perf_counter())
+        except Exception as e:                 # noqa: BLE001
+            torch.cuda.synchronize(dev)
+            launches = l1
+            _NOT_CAPTURABLE.add(_cb_key(fun, jac))
+            warnings.warn("bounded_lsq_b200: the callbacks could not be "
+                          "captured into a CUDA graph (%r); the tail of the "
+                          "batch runs as eager rounds" % (e,), RuntimeWarning)
+            return r, False
+        per_replay = launches - l1
+        launches = l1
+        while True:
+            g.replay()
+            launches += per_replay
+            r += GRAPH_ROUNDS
+            if int(count.item()) == 0 or rounds + r > max_nfev + 1:
+                if dbg:
+                    tt.append(time.perf_counter())
+                    print("# graph tail A=%d: begin %.2f capture %.2f end %.2f "
+                          "replays(%d rounds) %.2f ms" % (
+                              A, *[(b - a) * 1e3 for a, b in zip(tt, tt[1:])][:3],
+                              r, (tt[-1] - tt[-2]) * 1e3), file=sys.stderr)
+                return r, True
+
+    if graph_tail_rounds is None:                  # BLSQ_GRAPH_TAIL=0 turns it off
+        graph_tail_rounds = int(os.environ.get("BLSQ_GRAPH_TAIL", "8"))
+    use_graph = (graph_tail_rounds > 0 and X0.is_cuda and trace is None
+                 and timers is None
+                 and _cb_key(fun, jac) not in _NOT_CAPTURABLE)
+    GRAPH_ROUNDS = int(graph_tail_rounds)
+    while A > 0:
+        one_round(A, idx, idx32, first, nrun)
         first = 0
         rounds += 1
         if trace is not None:
@@ -226,9 +354,7 @@ def solve_batched(lib, method, fun, jac, X0, lb, ub, ftol, xtol, gtol,
         # bandwidth-sized, every 4th once they are launch-latency sized
         every = check_every if A > tail_below else max(check_every, 4)
         if rounds % every == 0 or rounds >= max_nfev:
-            lib.call("blsq_count_running", A, ip, istate.data_ptr(),
-                     count.data_ptr(), stream)
-            launches += 1
+            count_running(A, idx32)
             nrun = int(count.item())                  # the one host sync
             if nrun == 0:
                 break
@@ -242,6 +368,12 @@ def solve_batched(lib, method, fun, jac, X0, lb, ub, ftol, xtol, gtol,
                 if Xjac is not None:
                     Xjac[:nrun] = Xjac[:A].index_select(0, sel)
                 A = nrun
+            if use_graph and A <= tail_below:
+                r, done = graph_tail(A, idx, idx32, nrun)
+                rounds += r
+                if done:
+                    break
+                use_graph = False                     # not capturable: eager
         if rounds > max_nfev + 1:                     # cannot happen
             raise RuntimeError("batched driver failed to terminate")
 

@@ -44,12 +44,23 @@ namespace {
 #define BLSQ_ROUND_MINB 4
 #endif
 
-// rows per lane held in registers by lin_kernel
+// rows per lane held in registers by lin_kernel, and the register budget:
+// N <= 4: 8 rows x 5 columns at 128 registers (4 CTAs / SM); N = 5, 6: 8 rows
+// x 7 columns at 168 registers (3 CTAs / SM) -- two problems per warp at
+// m = 128 halve the shuffle/sqrt instructions per problem, which is what the
+// kernel is bound by (profiles/r1_c3_lin_kernel_ncu.md); N = 7, 8: 4 rows.
 #ifndef BLSQ_RPL_SMALL
 #define BLSQ_RPL_SMALL 8
 #endif
+#ifndef BLSQ_RPL_MID
+#define BLSQ_RPL_MID 8
+#endif
+#ifndef BLSQ_LIN_MINB_MID
+#define BLSQ_LIN_MINB_MID 3
+#endif
 template <int N> struct LinCfg {
-    static constexpr int RPL = (N <= 4) ? BLSQ_RPL_SMALL : 4;
+    static constexpr int RPL = (N <= 4) ? BLSQ_RPL_SMALL : (N <= 6 ? BLSQ_RPL_MID : 4);
+    static constexpr int MINB = (N <= 4 || RPL <= 4) ? BLSQ_LIN_MINB : BLSQ_LIN_MINB_MID;
 };
 
 template <int G>
@@ -60,6 +71,21 @@ __device__ __forceinline__ double group_sum(double v) {
     return v;
 }
 
+// 1/sqrt(d), sqrt(d) and 1/d for the column norms of the Gram-Schmidt sweep
+// from ONE reciprocal square root (MUFU.RSQ64H + Newton) instead of a double
+// sqrt and a double division; each is within ~1 ulp.  d <= 0 -> zeros.
+__device__ __forceinline__ void norm_terms(double d, double& r, double& inv_r, double& inv_d) {
+    if (d > 0.0) {
+        double y = rsqrt(d);
+        double rr = d * y;
+        rr = fma(fma(-rr, rr, d), 0.5 * y, rr);        // one Newton step on sqrt
+        y = fma(fma(-rr, y, 1.0), y, y);               // and on 1/sqrt
+        r = rr; inv_r = y; inv_d = y * y;
+    } else {
+        r = sqrt(d); inv_r = 0.0; inv_d = 0.0;         // 0 or NaN as before
+    }
+}
+
 template <int N> struct PtrList { const double* p[2 * N]; };   // 2 per coordinate (3-point)
 
 // One group of G lanes (G = 8, 16 or 32) per problem; row (base + s*G + lane)
@@ -68,14 +94,19 @@ template <int N> struct PtrList { const double* p[2 * N]; };   // 2 per coordina
 // F at the i-th perturbed batch, (A, m); dx is (A, n).  MODE 2: 3-point
 // differences, Fpert.p[2i], p[2i+1] the two batches of coordinate i, dx is
 // (A, 2n): denominators, then the one-sided flags (blsq_fd3_points).
-template <int N, int G, int MODE>
-__global__ void __launch_bounds__(BLSQ_LIN_THREADS, BLSQ_LIN_MINB)
+// MULTI: m > G * RPL, the rows are folded in chunk by chunk with the running
+// triangle carried in one extra register row; otherwise all rows are resident,
+// g / f.f are reduced and written before the sweep and row k of the triangle
+// is stored by lane k as soon as it exists (fewer live registers).
+template <int N, int G, int MODE, bool MULTI>
+__global__ void __launch_bounds__(BLSQ_LIN_THREADS, LinCfg<N>::MINB)
 lin_kernel(int64_t A, const int32_t* __restrict__ idx, int m,
            const double* __restrict__ F, const double* __restrict__ J,
            PtrList<N> Fpert, const double* __restrict__ dx,
            const int32_t* __restrict__ istate, double* __restrict__ lin) {
     constexpr int RPL = LinCfg<N>::RPL;
     constexpr int C = N + 1;                      // columns of [J | f]
+    constexpr int AR = MULTI ? RPL + 1 : RPL;     // + carried row of the triangle
     typedef LinRec<N> L;
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t slot = tid / G;
@@ -90,90 +121,94 @@ lin_kernel(int64_t A, const int32_t* __restrict__ idx, int m,
 
     const double* Fp = F + slot * (int64_t)m;
     const double* Jp = (MODE == 0) ? J + slot * (int64_t)m * N : nullptr;
-    double dxj[N];
-    bool onej[N];
-    if (MODE == 1) {
-#pragma unroll
-        for (int j = 0; j < N; j++)
-            dxj[j] = valid ? 1.0 / dx[slot * N + j] : 1.0;   // reciprocal once
-    }
-    if (MODE == 2) {
-#pragma unroll
-        for (int j = 0; j < N; j++) {
-            dxj[j] = valid ? 1.0 / dx[slot * 2 * N + j] : 1.0;
-            onej[j] = valid ? dx[slot * 2 * N + N + j] != 0.0 : false;
-        }
-    }
+    double* out = lin + slot * (int64_t)L::SIZE;
 
-    double a[RPL + 1][C];        // a[RPL] = carried row of the running triangle
-    double myrow[C];             // row `lane` (< N) of the triangle, [.. | qtf]
+    double a[AR][C];
+    double myrow[MULTI ? C : 1];  // MULTI: row `lane` (< N) of the triangle, [.. | qtf]
     double gp[N], objp = 0.0;
 #pragma unroll
     for (int j = 0; j < N; j++) gp[j] = 0.0;
+    if (MULTI) {
 #pragma unroll
-    for (int j = 0; j < C; j++) { myrow[j] = 0.0; a[RPL][j] = 0.0; }
-    const bool multi = m > G * RPL;
+        for (int j = 0; j < C; j++) { myrow[j] = 0.0; a[AR - 1][j] = 0.0; }
+    }
 
-    for (int base = 0; base < m; base += G * RPL) {
+    for (int base = 0; base < (MULTI ? m : 1); base += G * RPL) {
         const bool full = all_valid && (base + G * RPL <= m);   // warp-uniform
         // ---- load this chunk ----
-#pragma unroll
-        for (int s = 0; s < RPL; s++) {
-            int row = base + s * G + lane;
-            bool ok = full || (valid && row < m);
-            if (ok) {
-                if (MODE == 0) {
-                    const double* rp = Jp + (int64_t)row * N;
-                    if (N % 2 == 0) {
-#pragma unroll
-                        for (int j = 0; j < N; j += 2) {
-                            double2 t = __ldcs(reinterpret_cast<const double2*>(rp + j));
-                            a[s][j] = t.x;
-                            a[s][j + 1] = t.y;
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < N; j++) a[s][j] = __ldcs(rp + j);
-                    }
-                } else if (MODE == 1) {
-#pragma unroll
-                    for (int j = 0; j < N; j++)
-                        a[s][j] = __ldcs(Fpert.p[j] + slot * (int64_t)m + row);
-                }
-                a[s][N] = __ldcs(Fp + row);
-                if (MODE == 2) {
-                    // scipy _dense_difference, '3-point': f2 - f1 (central) or
-                    // -3 f0 + 4 f1 - f2 (one sided), in NumPy's evaluation order
-                    const double f0 = a[s][N];
-#pragma unroll
-                    for (int j = 0; j < N; j++) {
-                        const double f1 = __ldcs(Fpert.p[2 * j] + slot * (int64_t)m + row);
-                        const double f2 = __ldcs(Fpert.p[2 * j + 1] + slot * (int64_t)m + row);
-                        a[s][j] = onej[j] ? ((-3.0 * f0 + 4 * f1) - f2) : (f2 - f1);
-                    }
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < C; j++) a[s][j] = 0.0;
-            }
-        }
-        if (MODE == 1) {
-            // scipy _dense_difference: J[:, i] = (f(x + h_i e_i) - f0) / dx_i,
-            // as a multiplication by 1/dx_i (<= 1 ulp from the quotient, far
-            // below the 1e-8 truncation noise of the difference itself);
-            // rows that were not loaded hold zeros: (0 - 0) * c = 0
-#pragma unroll
-            for (int s = 0; s < RPL; s++) {
+        {
+            double dxj[N];
+            bool onej[N];
+            if (MODE == 1) {
 #pragma unroll
                 for (int j = 0; j < N; j++)
-                    a[s][j] = (a[s][j] - a[s][N]) * dxj[j];
+                    dxj[j] = valid ? 1.0 / dx[slot * N + j] : 1.0;   // reciprocal once
             }
-        }
-        if (MODE == 2) {
+            if (MODE == 2) {
+#pragma unroll
+                for (int j = 0; j < N; j++) {
+                    dxj[j] = valid ? 1.0 / dx[slot * 2 * N + j] : 1.0;
+                    onej[j] = valid ? dx[slot * 2 * N + N + j] != 0.0 : false;
+                }
+            }
 #pragma unroll
             for (int s = 0; s < RPL; s++) {
+                int row = base + s * G + lane;
+                bool ok = full || (valid && row < m);
+                if (ok) {
+                    if (MODE == 0) {
+                        const double* rp = Jp + (int64_t)row * N;
+                        if (N % 2 == 0) {
 #pragma unroll
-                for (int j = 0; j < N; j++) a[s][j] *= dxj[j];
+                            for (int j = 0; j < N; j += 2) {
+                                double2 t = __ldcs(reinterpret_cast<const double2*>(rp + j));
+                                a[s][j] = t.x;
+                                a[s][j + 1] = t.y;
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < N; j++) a[s][j] = __ldcs(rp + j);
+                        }
+                    } else if (MODE == 1) {
+#pragma unroll
+                        for (int j = 0; j < N; j++)
+                            a[s][j] = __ldcs(Fpert.p[j] + slot * (int64_t)m + row);
+                    }
+                    a[s][N] = __ldcs(Fp + row);
+                    if (MODE == 2) {
+                        // scipy _dense_difference, '3-point': f2 - f1 (central) or
+                        // -3 f0 + 4 f1 - f2 (one sided), in NumPy's evaluation order
+                        const double f0 = a[s][N];
+#pragma unroll
+                        for (int j = 0; j < N; j++) {
+                            const double f1 = __ldcs(Fpert.p[2 * j] + slot * (int64_t)m + row);
+                            const double f2 = __ldcs(Fpert.p[2 * j + 1] + slot * (int64_t)m + row);
+                            a[s][j] = onej[j] ? ((-3.0 * f0 + 4 * f1) - f2) : (f2 - f1);
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < C; j++) a[s][j] = 0.0;
+                }
+            }
+            if (MODE == 1) {
+                // scipy _dense_difference: J[:, i] = (f(x + h_i e_i) - f0) / dx_i,
+                // as a multiplication by 1/dx_i (<= 1 ulp from the quotient, far
+                // below the 1e-8 truncation noise of the difference itself);
+                // rows that were not loaded hold zeros: (0 - 0) * c = 0
+#pragma unroll
+                for (int s = 0; s < RPL; s++) {
+#pragma unroll
+                    for (int j = 0; j < N; j++)
+                        a[s][j] = (a[s][j] - a[s][N]) * dxj[j];
+                }
+            }
+            if (MODE == 2) {
+#pragma unroll
+                for (int s = 0; s < RPL; s++) {
+#pragma unroll
+                    for (int j = 0; j < N; j++) a[s][j] *= dxj[j];
+                }
             }
         }
         // ---- g = J^T f and f.f on the raw rows (trf.py:244, 229) ----
@@ -183,10 +218,20 @@ lin_kernel(int64_t A, const int32_t* __restrict__ idx, int m,
             for (int j = 0; j < N; j++) gp[j] = fma(a[s][j], a[s][N], gp[j]);
             objp = fma(a[s][N], a[s][N], objp);
         }
-        // ---- carry: row k of the running triangle lives on lane k ----
-        if (multi) {
+        if (!MULTI) {
+            // all rows are here: finish g and f.f now and free their registers
 #pragma unroll
-            for (int j = 0; j < C; j++) a[RPL][j] = (lane < N) ? myrow[j] : 0.0;
+            for (int j = 0; j < N; j++) {
+                const double gj = group_sum<G>(gp[j]);
+                if (valid && lane == j) out[L::G + j] = gj;
+            }
+            const double ob = group_sum<G>(objp);
+            if (valid && lane == N % G) out[L::OBJ] = ob;
+        }
+        // ---- carry: row k of the running triangle lives on lane k ----
+        if (MULTI) {
+#pragma unroll
+            for (int j = 0; j < C; j++) a[AR - 1][j] = (lane < N) ? myrow[j] : 0.0;
         }
         // ---- modified Gram-Schmidt on the stacked (carry + chunk) rows ----
 #pragma unroll
@@ -196,48 +241,53 @@ lin_kernel(int64_t A, const int32_t* __restrict__ idx, int m,
             for (int j = k; j < C; j++) {
                 double acc = 0.0;
 #pragma unroll
-                for (int s = 0; s < RPL; s++) acc = fma(a[s][k], a[s][j], acc);
-                if (multi) acc = fma(a[RPL][k], a[RPL][j], acc);
+                for (int s = 0; s < AR; s++) acc = fma(a[s][k], a[s][j], acc);
                 dts[j] = group_sum<G>(acc);
             }
-            const double dk = dts[k];
-            const bool pos = dk > 0.0;
-            const double rkk = sqrt(dk);
-            const double inv_dk = pos ? 1.0 / dk : 0.0;
-            const double inv_rkk = rkk * inv_dk;           // 1/sqrt(dk)
-            if (lane == k) {
+            double rkk, inv_rkk, inv_dk;
+            norm_terms(dts[k], rkk, inv_rkk, inv_dk);
+            if (MULTI) {
+                if (lane == k) {
 #pragma unroll
-                for (int j = 0; j < C; j++) myrow[j] = 0.0;
-                myrow[k] = rkk;
+                    for (int j = 0; j < C; j++) myrow[j] = 0.0;
+                    myrow[k] = rkk;
+                }
+            } else if (valid && lane == k) {
+                out[L::R + tri_index<N>(k, k)] = rkk;
             }
 #pragma unroll
             for (int j = k + 1; j < C; j++) {
                 const double coef = dts[j] * inv_dk;
-                if (lane == k) myrow[j] = dts[j] * inv_rkk;
+                const double rkj = dts[j] * inv_rkk;
+                if (MULTI) {
+                    if (lane == k) myrow[j] = rkj;
+                } else if (valid && lane == k) {
+                    if (j < N) out[L::R + tri_index<N>(k, j)] = rkj;
+                    else out[L::QTF + k] = rkj;
+                }
 #pragma unroll
-                for (int s = 0; s < RPL; s++)
+                for (int s = 0; s < AR; s++)
                     a[s][j] = fma(-coef, a[s][k], a[s][j]);
-                if (multi) a[RPL][j] = fma(-coef, a[RPL][k], a[RPL][j]);
             }
         }
     }
+    if (MULTI) {
 #pragma unroll
-    for (int j = 0; j < N; j++) gp[j] = group_sum<G>(gp[j]);
-    objp = group_sum<G>(objp);
-
-    if (valid) {
-        double* out = lin + slot * (int64_t)L::SIZE;
-        // lanes 0..N-1 write one row of the triangle each (+ their g, qtf)
+        for (int j = 0; j < N; j++) gp[j] = group_sum<G>(gp[j]);
+        objp = group_sum<G>(objp);
+        if (valid) {
+            // lanes 0..N-1 write one row of the triangle each (+ their g, qtf)
 #pragma unroll
-        for (int k = 0; k < N; k++) {
-            if (lane == k) {
+            for (int k = 0; k < N; k++) {
+                if (lane == k) {
 #pragma unroll
-                for (int j = k; j < N; j++) out[L::R + tri_index<N>(k, j)] = myrow[j];
-                out[L::QTF + k] = myrow[N];
-                out[L::G + k] = gp[k];
+                    for (int j = k; j < N; j++) out[L::R + tri_index<N>(k, j)] = myrow[j];
+                    out[L::QTF + k] = myrow[N];
+                    out[L::G + k] = gp[k];
+                }
             }
+            if (lane == N % G) out[L::OBJ] = objp;
         }
-        if (lane == N % G) out[L::OBJ] = objp;
     }
 }
 
@@ -376,7 +426,7 @@ __global__ void count_running_kernel(int64_t B,
     if ((threadIdx.x & 31) == 0 && bal) atomicAdd(count, __popc(bal));
 }
 
-template <int N, int G>
+template <int N, int G, bool MULTI>
 int launch_lin_g(int64_t A, const int32_t* idx, int m, const double* F,
                  const double* J, const PtrList<N>& pl, const double* dx,
                  int jac_mode, const int32_t* istate, double* lin,
@@ -385,13 +435,13 @@ int launch_lin_g(int64_t A, const int32_t* idx, int m, const double* F,
     int64_t blocks = (threads + BLSQ_LIN_THREADS - 1) / BLSQ_LIN_THREADS;
     if (blocks > 0x7fffffff) return BLSQ_E_UNSUPPORTED;
     if (jac_mode == 0)
-        lin_kernel<N, G, 0><<<(unsigned)blocks, BLSQ_LIN_THREADS, 0, s>>>(
+        lin_kernel<N, G, 0, MULTI><<<(unsigned)blocks, BLSQ_LIN_THREADS, 0, s>>>(
             A, idx, m, F, J, pl, dx, istate, lin);
     else if (jac_mode == 1)
-        lin_kernel<N, G, 1><<<(unsigned)blocks, BLSQ_LIN_THREADS, 0, s>>>(
+        lin_kernel<N, G, 1, MULTI><<<(unsigned)blocks, BLSQ_LIN_THREADS, 0, s>>>(
             A, idx, m, F, J, pl, dx, istate, lin);
     else
-        lin_kernel<N, G, 2><<<(unsigned)blocks, BLSQ_LIN_THREADS, 0, s>>>(
+        lin_kernel<N, G, 2, MULTI><<<(unsigned)blocks, BLSQ_LIN_THREADS, 0, s>>>(
             A, idx, m, F, J, pl, dx, istate, lin);
     BLSQ_LAUNCH_CHECK();
     return 0;
@@ -408,10 +458,12 @@ int launch_lin(int64_t A, const int32_t* idx, int m, const double* F,
     for (int j = 0; j < 2 * N; j++) pl.p[j] = (j < np) ? Fp_host[j] : nullptr;
     // smallest lane group whose registers hold all m rows (else 32 + chunks)
     if (m <= 8 * RPL)
-        return launch_lin_g<N, 8>(A, idx, m, F, J, pl, dx, jac_mode, istate, lin, s);
+        return launch_lin_g<N, 8, false>(A, idx, m, F, J, pl, dx, jac_mode, istate, lin, s);
     if (m <= 16 * RPL)
-        return launch_lin_g<N, 16>(A, idx, m, F, J, pl, dx, jac_mode, istate, lin, s);
-    return launch_lin_g<N, 32>(A, idx, m, F, J, pl, dx, jac_mode, istate, lin, s);
+        return launch_lin_g<N, 16, false>(A, idx, m, F, J, pl, dx, jac_mode, istate, lin, s);
+    if (m <= 32 * RPL)
+        return launch_lin_g<N, 32, false>(A, idx, m, F, J, pl, dx, jac_mode, istate, lin, s);
+    return launch_lin_g<N, 32, true>(A, idx, m, F, J, pl, dx, jac_mode, istate, lin, s);
 }
 
 template <int N>

@@ -603,8 +603,9 @@ int blsq_tall_gram(int pass, int64_t m, int n, const double* J, const double* f,
     if (pass == 2 && (!Rinv || !f)) return BLSQ_E_BADARG;
     if (pass == 2 || sstride < 1) sstride = 1;
     if (!f) f = J;                                  /* pass 1 never reads f */
-    // rows are moved by 16-byte-granular bulk copies
-    if (n < 2 || n > 256 || (n & 1)) return BLSQ_E_UNSUPPORTED;
+    // rows are moved by 16-byte-granular bulk copies: a quarter tile is 16
+    // rows = 128 n bytes, so any n keeps source and size 16-byte aligned
+    if (n < 2 || n > 256) return BLSQ_E_UNSUPPORTED;
     if (((uintptr_t)J & 15) || ((uintptr_t)f & 15)) return BLSQ_E_BADARG;
     cudaStream_t s = (cudaStream_t)stream;
 #define BLSQ_GRAM_CASE(NB_)                                                         \

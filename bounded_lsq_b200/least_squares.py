@@ -242,6 +242,10 @@ def least_squares(fun, x0, jac='2-point', bounds=(-float('inf'), float('inf')),
                           max_nfev, scaling, diff_step, args, kwargs, options)
 
     fun_b, jac_b = _single_callbacks(fun, jac, tuple(args), dict(kwargs), dev)
+    # single-problem callbacks are arbitrary user Python (often with host
+    # round trips): no CUDA-graph capture unless asked for
+    options = dict(options)
+    options.setdefault("graph_tail_rounds", 0)
     out = solve_batched(lib, method, fun_b, jac_b, X0, lb, ub, ftol, xtol,
                         gtol, max_nfev, scaling, diff_step=diff_step,
                         **options)

@@ -21,6 +21,18 @@ except Exception:  # pragma: no cover
     torch = None
 
 
+def _dev_const(model, X):
+    """model.t on X's device, uploaded once (a host-to-device copy per
+    callback would also make the callback impossible to capture in a CUDA
+    graph)."""
+    cache = model.__dict__.setdefault("_t_dev", {})
+    key = (X.device, X.dtype)
+    t = cache.get(key)
+    if t is None:
+        t = cache[key] = torch.as_tensor(model.t, dtype=X.dtype, device=X.device)
+    return t
+
+
 # ------------------------------------------------------------------ C2 ----
 
 class ExpDecay2:
@@ -66,12 +78,12 @@ class ExpDecay2:
 
     # batched, torch
     def fun_t(self, X, y):
-        t = torch.as_tensor(self.t, dtype=X.dtype, device=X.device)
+        t = _dev_const(self, X)
         return (X[:, 0:1] * torch.exp(-X[:, 1:2] * t) +
                 X[:, 2:3] * torch.exp(-X[:, 3:4] * t) - y)
 
     def jac_t(self, X, y=None):
-        t = torch.as_tensor(self.t, dtype=X.dtype, device=X.device)
+        t = _dev_const(self, X)
         e1 = torch.exp(-X[:, 1:2] * t)
         e2 = torch.exp(-X[:, 3:4] * t)
         J = torch.empty((X.shape[0], self.m, 4), dtype=X.dtype,
@@ -119,7 +131,7 @@ class GaussPeak:
         return x[0] * np.exp(-0.5 * z * z) + x[3] + x[4] * t + x[5] * t * t - y
 
     def fun_t(self, X, y):
-        t = torch.as_tensor(self.t, dtype=X.dtype, device=X.device)
+        t = _dev_const(self, X)
         z = (t - X[:, 1:2]) / X[:, 2:3]
         return (X[:, 0:1] * torch.exp(-0.5 * z * z) + X[:, 3:4] +
                 X[:, 4:5] * t + X[:, 5:6] * t * t - y)

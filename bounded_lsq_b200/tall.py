@@ -105,8 +105,8 @@ def solve_tall(lib, method, fun, jac, x0, lb, ub, ftol, xtol, gtol, max_nfev,
     dev = x0.device
     f64 = torch.float64
     n = x0.shape[0]
-    if n > 256 or n % 2:
-        raise ValueError("tall mode supports even n <= 256")
+    if n > 256:
+        raise ValueError("tall mode supports n <= 256")
     lay = lib.tall_layout(n)
     gather = _Gather(group)
     nranks = gather.nranks

@@ -228,6 +228,40 @@ def check_compaction_invariance(lib, dev):
         assert bits(r.nfev.cpu().numpy(), base.nfev.cpu().numpy()), opts
 
 
+def check_graph_tail_invariance(lib, dev):
+    """The CUDA-graph tail (rounds captured once and replayed) must give the
+    same bits as eager rounds, with torch callbacks, with the 2-point path, and
+    must fall back to eager rounds when a callback cannot be captured."""
+    out = {}
+    for cfg, method, jac in (("c2", "trf", "exact"), ("c3", "dogbox", "2-point")):
+        model = MODELS[cfg]()
+        B = 3000
+        _, y = model.make_data(B, seed=77)
+        yt = T(y, dev)
+        X0 = T(np.tile(model.x0, (B, 1)), dev)
+        j = model.jac_t if jac == "exact" else jac
+
+        def solve(fun=model.fun_t, **opts):
+            return least_squares_batched(
+                fun, X0, jac=j, bounds=(model.lb, model.ub), method=method,
+                args=(PerProblem(yt),), options=opts, _lib=lib)
+
+        def syncing_fun(X, yy):
+            float(X[0, 0].item())              # host sync: not capturable
+            return model.fun_t(X, yy)
+
+        base = solve(graph_tail_rounds=0)
+        for label, r in (("graph8", solve()),
+                         ("graph3", solve(graph_tail_rounds=3, tail_below=2000)),
+                         ("fallback", solve(fun=syncing_fun))):
+            for fld in ("x", "obj_value", "status", "nfev", "njev", "active_mask"):
+                assert bits(getattr(r, fld).cpu().numpy(),
+                            getattr(base, fld).cpu().numpy()), (cfg, label, fld)
+            out[(cfg, label)] = (r.rounds, base.rounds)
+        assert int((base.status > 0).sum()) == B
+    return out
+
+
 def check_per_problem_bounds(lib, dev):
     """(B, n) bounds give the same answers as shared (n,) bounds."""
     model = ExpDecay2()
@@ -421,7 +455,8 @@ def check_tall_factor(lib, dev):
     gen = torch.Generator(device="cpu").manual_seed(5)
     rel = lambda a, b: float((a - b).norm() / b.norm())        # noqa: E731
     for (m, n, shards) in ((1000, 10, 1), (4099, 16, 2), (20001, 64, 3),
-                           (7777, 24, 1), (5000, 100, 2), (3000, 130, 1)):
+                           (7777, 24, 1), (5000, 100, 2), (3000, 130, 1),
+                           (901, 9, 1), (6005, 33, 2), (2047, 67, 1)):
         J = torch.randn((m, n), dtype=torch.float64, generator=gen).to(dev)
         f = torch.randn(m, dtype=torch.float64, generator=gen).to(dev)
         out = tall_factor(lib, J, f, shards)
@@ -549,3 +584,35 @@ def check_tall_options_vs_oracle(lib, dev, m=3000, n=12):
                     (method, label, s)
             assert res.jac.shape == (m, n)
     return out
+
+
+# ------------------------------------------------ benchmark driver (8f #3) --
+
+def check_benchmark_table(lib, dev, out_path):
+    """benchmarks/run_benchmarks.py (the reference's table from this path):
+    every row of the bounded table must carry the reference's nfev / status /
+    value / number of active bounds (golden corpus)."""
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location(
+        "blsq_run_benchmarks", os.path.join(root, "benchmarks", "run_benchmarks.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    rows = mod.main([str(out_path), "-b"], lib=lib, dev=dev)
+    z = np.load(os.path.join(GOLDEN, "corpus.npz"))
+    checked = unsupported = 0
+    for name, meth, r in rows:
+        if r is None:
+            unsupported += 1
+            continue
+        if name in CHAOTIC or name.split("_")[0] in CHAOTIC:
+            continue
+        obj, status, nfev, njev, opt, ntr = z[f"{name}|{meth}|exact|1|scalars"]
+        mask = z[f"{name}|{meth}|exact|1|mask"]
+        assert r[4] == int(status) and r[0] == int(nfev), (name, meth, r)
+        assert abs(r[2] - obj) <= 1e-8 * obj + 1e-18, (name, meth, r, obj)
+        assert r[3] == int(np.count_nonzero(mask)), (name, meth, r)
+        checked += 1
+    text = open(out_path).read()
+    assert "Bounded problems" in text and "g norm" in text
+    return dict(checked=checked, unsupported=unsupported)

@@ -387,7 +387,7 @@ int blsq_tall_sample_stride(int64_t m, int n) {
 
 int blsq_tall_gram(int pass, int64_t m, int n, const double* J, const double* f,
                    const double* rinvp, int sstride, double*, double* out, void*) {
-    if (n < 2 || n > 256 || (n & 1)) return BLSQ_E_UNSUPPORTED;
+    if (n < 2 || n > 256) return BLSQ_E_UNSUPPORTED;
     std::vector<double> X;
     if (pass == 2) {
         // unpack the fragment-ordered R1^-1

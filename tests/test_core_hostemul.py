@@ -61,3 +61,9 @@ def test_tall_golden(lib, tag, method):
 
 def test_tall_options_vs_oracle(lib):
     print(cases.check_tall_options_vs_oracle(lib, torch.device("cpu")))
+
+
+def test_benchmark_table(lib, tmp_path):
+    st = cases.check_benchmark_table(lib, DEV, tmp_path / "table.txt")
+    print(st)
+    assert st["checked"] >= 30

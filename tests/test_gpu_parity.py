@@ -46,6 +46,10 @@ def test_compaction_invariance(lib, dev):
     cases.check_compaction_invariance(lib, dev)
 
 
+def test_graph_tail_invariance(lib, dev):
+    print(cases.check_graph_tail_invariance(lib, dev))
+
+
 def test_per_problem_bounds(lib, dev):
     cases.check_per_problem_bounds(lib, dev)
 
@@ -193,3 +197,9 @@ def test_tall_options_vs_oracle(lib, dev):
     """scaling='jac' / vector scaling / jac='2-point' in tall mode, oracle run
     on the GPU box's host CPU."""
     print(cases.check_tall_options_vs_oracle(lib, dev))
+
+
+def test_benchmark_table(lib, dev, tmp_path):
+    st = cases.check_benchmark_table(lib, dev, tmp_path / "table.txt")
+    print(st)
+    assert st["checked"] >= 30
