@@ -33,10 +33,11 @@ SIGNATURES = {
     "blsq_find_intersection": [_l, _i, _p, _p, _p, _p, _i, _p, _p, _p, _p],
     "blsq_fd2_points": [_l, _p, _i, _p, _p, _p, _i, _d, _p, _p, _p],
     "blsq_fd3_points": [_l, _p, _i, _p, _p, _p, _i, _d, _p, _p, _p],
+    "blsq_compact_batched": [_l, _p, _p, _i, _p, _p, _p, _p, _p, _p, _p, _p],
     "blsq_init_batched": [_i, _l, _i, _p, _p, _p, _i, _p, _p, _p, _p],
     "blsq_linearise_batched": [_l, _p, _i, _i, _p, _p, _p, _p, _i, _p, _p, _p],
     "blsq_round_batched": [_i, _l, _p, _i, _i, _p, _p, _p, _p, _i, _p,
-                           _d, _d, _d, _i, _i, _p, _p, _p, _p, _p],
+                           _d, _d, _d, _i, _i, _p, _p, _p, _p, _p, _p],
     "blsq_dogbox_on_bound": [_l, _i, _p, _p, _p],
     "blsq_count_running": [_l, _p, _p, _p, _p],
     "blsq_model_expdecay2": [_l, _p, _i, _p, _p, _p, _p, _p, _p],
@@ -86,6 +87,9 @@ class Lib:
         self._dll = C.CDLL(path)
         self._dll.blsq_error_string.restype = C.c_char_p
         self._dll.blsq_error_string.argtypes = [_i]
+        if hasattr(self._dll, "blsq_compact_work_size"):
+            self._dll.blsq_compact_work_size.argtypes = [_l]
+            self._dll.blsq_compact_work_size.restype = _l
         for name in ("blsq_tall_gram_work_size", "blsq_tall_fac_size",
                      "blsq_tall_record_size"):
             if hasattr(self._dll, name):

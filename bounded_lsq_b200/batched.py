@@ -45,7 +45,11 @@ class PerProblem:
 def _gather_args(args, kwargs, idx):
     def g(a):
         if isinstance(a, PerProblem):
-            return a.tensor if idx is None else a.tensor.index_select(0, idx)
+            if idx is None:
+                return a.tensor
+            if isinstance(idx, slice):             # contiguous range (prologue)
+                return a.tensor[idx]
+            return a.tensor.index_select(0, idx)
         return a
     return tuple(g(a) for a in args), {k: g(v) for k, v in kwargs.items()}
 
@@ -62,11 +66,13 @@ class BatchedCallbacks:
     def _call(self, fn, X, idx):
         if getattr(fn, "blsq_indexed", False):
             # indexed protocol: raw per-problem tensors + the active ids
-            a = tuple(v.tensor if isinstance(v, PerProblem) else v
-                      for v in self.args)
-            k = {n: (v.tensor if isinstance(v, PerProblem) else v)
-                 for n, v in self.kwargs.items()}
-            return fn(X, idx, *a, **k)
+            sl = idx if isinstance(idx, slice) else slice(None)
+
+            def raw(v):
+                return v.tensor[sl] if isinstance(v, PerProblem) else v
+            a = tuple(raw(v) for v in self.args)
+            k = {n: raw(v) for n, v in self.kwargs.items()}
+            return fn(X, None if isinstance(idx, slice) else idx, *a, **k)
         # the active set only changes when the driver compacts it: gather the
         # per-problem data once per compaction, not once per callback
         if self._gathered[0] is not idx or idx is None:
@@ -104,6 +110,12 @@ def _graph_pool(dev):
     return p
 
 
+# the allocator drops a pool when the last graph that used it is destroyed:
+# the most recent tail graph of each device is kept alive until the next one
+# has been captured
+_LAST_GRAPH = {}
+
+
 # callbacks whose capture failed once are not tried again (a failed capture
 # costs a device synchronisation and an allocator flush)
 _NOT_CAPTURABLE = set()
@@ -129,7 +141,8 @@ def _as_f64(t, like, what):
 def solve_batched(lib, method, fun, jac, X0, lb, ub, ftol, xtol, gtol,
                   max_nfev, scaling, diff_step=None, check_every=1,
                   compact_below=0.75, tail_below=8192, trace=None,
-                  timers=None, graph_tail_rounds=None):
+                  timers=None, graph_tail_rounds=None, prologue=None,
+                  prologue_rounds=6):
     """Run ``method`` ('trf' | 'dogbox') on B problems.
 
     fun(X, idx) -> (A, m); jac is a callable jac(X, idx) -> (A, m, n) or the
@@ -169,6 +182,12 @@ def solve_batched(lib, method, fun, jac, X0, lb, ub, ftol, xtol, gtol,
         else None
     lin = torch.empty((B, LS), dtype=f64, device=dev)
     count = torch.zeros(1, dtype=torch.int32, device=dev)
+    # TRF: worklist of the problems that leave the Gauss-Newton shortcut
+    # (blsq_round_batched `work`); BLSQ_TRF_TWO_KERNELS=0 -> single kernel
+    rwork = None
+    if method == "trf" and os.environ.get("BLSQ_TRF_TWO_KERNELS", "1") != "0":
+        rwork = torch.empty(B + 1, dtype=torch.int32, device=dev)
+    rwork_ptr = None if rwork is None else rwork.data_ptr()
     if fd:
         Xp = torch.empty((npts, B, n), dtype=f64, device=dev)
         dx = torch.empty((B, 2 * n if fd3 else n), dtype=f64, device=dev)
@@ -197,18 +216,31 @@ def solve_batched(lib, method, fun, jac, X0, lb, ub, ftol, xtol, gtol,
 
     idx = None          # int64 for torch gathers
     idx32 = None        # int32 copy handed to the kernels
+    pong, flip, cwork = None, 0, None
     A = B
     first = 1
     m = None
     rounds = 0
     launches = 0
 
-    def one_round(A, idx, idx32, first, nrun):
-        """Callbacks + linearise + round for the A compacted slots."""
+    def one_round(A, idx, idx32, first, nrun, off=0):
+        """Callbacks + linearise + round for the A compacted slots (or, in the
+        streaming prologue, for the A problems starting at problem `off`)."""
         nonlocal m, launches
         stream = lib.stream(X0)            # the capture stream inside a graph
-        Xa = Xnew[:A]
-        Xj = Xa if (Xjac is None or first) else Xjac[:A]
+        Xa = Xnew[off:off + A]
+        Xj = Xa if (Xjac is None or first) else Xjac[off:off + A]
+        if idx is None and (off or A != B):
+            idx = slice(off, off + A)
+        # base pointers of this range of problems
+        p_ist = istate.data_ptr() + off * L.ISTATE_SIZE * 4
+        p_lin = lin.data_ptr() + off * LS * 8
+        p_st = state.data_ptr() + off * S * 8
+        p_x0 = X0.data_ptr() + off * n * 8
+        p_lb = lb.data_ptr() + off * bstride * 8
+        p_ub = ub.data_ptr() + off * bstride * 8
+        p_xn = Xnew.data_ptr() + off * n * 8
+        p_xj = None if Xjac is None else Xjac.data_ptr() + off * n * 8
         t0 = tick()
         F = _as_f64(fun(Xa, idx), X0, "fun")
         if F.dim() != 2 or F.shape[0] != A:
@@ -233,13 +265,12 @@ def solve_batched(lib, method, fun, jac, X0, lb, ub, ftol, xtol, gtol,
             tock("callbacks", t0, nrun)
             t0 = tick()
             lib.call("blsq_linearise_batched", A, ip, m, n, F.data_ptr(),
-                     J.data_ptr(), None, None, 0, istate.data_ptr(),
-                     lin.data_ptr(), stream)
+                     J.data_ptr(), None, None, 0, p_ist, p_lin, stream)
             tock("linearise", t0, nrun)
         else:
             Xpa = Xp.view(-1)[: npts * A * n].view(npts, A, n)
             lib.call("blsq_fd3_points" if fd3 else "blsq_fd2_points", A, ip, n,
-                     Xj.data_ptr(), lb.data_ptr(), ub.data_ptr(), bstride, rel,
+                     Xj.data_ptr(), p_lb, p_ub, bstride, rel,
                      Xpa.data_ptr(), dx.data_ptr(), stream)
             launches += 1
             Fp = []
@@ -253,18 +284,17 @@ def solve_batched(lib, method, fun, jac, X0, lb, ub, ftol, xtol, gtol,
             t0 = tick()
             lib.call("blsq_linearise_batched", A, ip, m, n, F.data_ptr(), None,
                      C.cast(plist, C.c_void_p), dx.data_ptr(), 2 if fd3 else 1,
-                     istate.data_ptr(), lin.data_ptr(), stream)
+                     p_ist, p_lin, stream)
             tock("linearise", t0, nrun)
         t0 = tick()
-        lib.call("blsq_round_batched", meth, A, ip, m, n, lin.data_ptr(),
-                 X0.data_ptr(), lb.data_ptr(), ub.data_ptr(), bstride, sc_ptr,
+        lib.call("blsq_round_batched", meth, A, ip, m, n, p_lin,
+                 p_x0, p_lb, p_ub, bstride, sc_ptr,
                  float(ftol), float(xtol), float(gtol), max_nfev, first,
-                 state.data_ptr(), istate.data_ptr(), Xnew.data_ptr(),
-                 None if Xjac is None else Xjac.data_ptr(), stream)
+                 p_st, p_ist, p_xn, p_xj, rwork_ptr, stream)
         tock("round", t0, nrun)
         if timers is not None:
             timers["shape"] = (n, m, LS, S)
-        launches += 2
+        launches += 2 if rwork is None else 3
 
     def count_running(A, idx32):
         nonlocal launches
@@ -291,9 +321,12 @@ def solve_batched(lib, method, fun, jac, X0, lb, ub, ftol, xtol, gtol,
         # back to cudaMalloc); capture_begin / capture_end on a side stream
         # do neither.
         dbg = os.environ.get("BLSQ_GRAPH_DEBUG")
+        # drain the (latency-sized) queue first: measured on the B200, a
+        # capture that starts while the eager round is still in flight costs
+        # ~16 ms more per solve than the microseconds this wait takes
+        torch.cuda.current_stream(dev).synchronize()
         if dbg:
             import time
-            torch.cuda.synchronize(dev)
             tt = [time.perf_counter()]
         g = torch.cuda.CUDAGraph()
         cur = torch.cuda.current_stream(dev)
@@ -313,6 +346,7 @@ def solve_batched(lib, method, fun, jac, X0, lb, ub, ftol, xtol, gtol,
                         tt.append(time.perf_counter())
                     g.capture_end()
             cur.wait_stream(side)
+            _LAST_GRAPH[dev] = g
             if dbg:
                 tt.append(time.perf_counter())
         except Exception as e:                 # noqa: BLE001
@@ -344,6 +378,18 @@ def solve_batched(lib, method, fun, jac, X0, lb, ub, ftol, xtol, gtol,
                  and timers is None
                  and _cb_key(fun, jac) not in _NOT_CAPTURABLE)
     GRAPH_ROUNDS = int(graph_tail_rounds)
+    if prologue:
+        # streaming start: the per-problem data arrives from the host in
+        # chunks; each chunk runs its first rounds alone while the next one is
+        # still on the wire, then the whole batch carries on in lock step
+        K = max(1, min(int(prologue_rounds), max_nfev))
+        for c0, c1, ev in prologue:
+            if ev is not None:
+                torch.cuda.current_stream(dev).wait_event(ev)
+            for r in range(K):
+                one_round(c1 - c0, None, None, 1 if r == 0 else 0, c1 - c0, off=c0)
+        first = 0
+        rounds = K
     while A > 0:
         one_round(A, idx, idx32, first, nrun)
         first = 0
@@ -359,14 +405,31 @@ def solve_batched(lib, method, fun, jac, X0, lb, ub, ftol, xtol, gtol,
             if nrun == 0:
                 break
             if nrun <= compact_below * A:
-                st = istate[:, 0] if idx is None else istate[idx, 0]
-                running = st == L.STATUS_RUNNING
-                sel = running.nonzero(as_tuple=False).squeeze(1)
-                idx = sel if idx is None else idx.index_select(0, sel)
-                idx32 = idx.to(torch.int32)
-                Xnew[:nrun] = Xnew[:A].index_select(0, sel)
-                if Xjac is not None:
-                    Xjac[:nrun] = Xjac[:A].index_select(0, sel)
+                # ordered compaction on the device (3 small launches, no host
+                # round trip) into the other half of a ping-pong pair
+                if pong is None:
+                    pong = [dict(X=torch.empty_like(Xnew),
+                                 J=None if Xjac is None else torch.empty_like(Xjac),
+                                 i32=torch.empty(A, dtype=torch.int32, device=dev),
+                                 i64=torch.empty(A, dtype=torch.int64, device=dev)),
+                            dict(X=Xnew, J=Xjac,
+                                 i32=torch.empty(A, dtype=torch.int32, device=dev),
+                                 i64=torch.empty(A, dtype=torch.int64, device=dev))]
+                    cwork = torch.empty(int(lib._dll.blsq_compact_work_size(A)),
+                                        dtype=torch.int32, device=dev)
+                o = pong[flip]
+                flip ^= 1
+                lib.call("blsq_compact_batched", A,
+                         None if idx32 is None else idx32.data_ptr(),
+                         istate.data_ptr(), n, Xnew.data_ptr(),
+                         None if Xjac is None else Xjac.data_ptr(),
+                         o["i32"].data_ptr(), o["i64"].data_ptr(),
+                         o["X"].data_ptr(),
+                         None if Xjac is None else o["J"].data_ptr(),
+                         cwork.data_ptr(), lib.stream(X0))
+                launches += 3
+                Xnew, Xjac = o["X"], o["J"]
+                idx, idx32 = o["i64"][:nrun], o["i32"][:nrun]
                 A = nrun
             if use_graph and A <= tail_below:
                 r, done = graph_tail(A, idx, idx32, nrun)

@@ -291,7 +291,11 @@ lin_kernel(int64_t A, const int32_t* __restrict__ idx, int m,
     }
 }
 
-template <int N, int METHOD>
+// MODE 0: the whole round in one kernel.  TRF with a worklist (work != null):
+// MODE 1 runs the round with the Gauss-Newton shortcut and appends the slots
+// that need the SVD route to work[1..] (work[0] = their number); MODE 2 then
+// finishes exactly those slots with dense warps (blsq_core.cuh trf_round_impl).
+template <int N, int METHOD, int MODE>
 __global__ void __launch_bounds__(BLSQ_ROUND_THREADS, BLSQ_ROUND_MINB)
 round_kernel(int64_t A, const int32_t* __restrict__ idx,
              const double* __restrict__ lin, const double* __restrict__ x0,
@@ -299,12 +303,16 @@ round_kernel(int64_t A, const int32_t* __restrict__ idx,
              int bstride, const double* __restrict__ scaling, SolveParams P,
              int first, double* __restrict__ state,
              int32_t* __restrict__ istate, double* __restrict__ Xnew,
-             double* __restrict__ Xjac) {
+             double* __restrict__ Xjac, int32_t* __restrict__ work) {
     typedef LinRec<N> L;
     constexpr int SS = (METHOD == BLSQ_METHOD_TRF) ? TrfState<N>::SIZE
                                                    : DogState<N>::SIZE;
     constexpr int XNEW = N;
-    const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (MODE == 2) {
+        if (slot >= work[0]) return;
+        slot = work[1 + slot];
+    }
     if (slot >= A) return;
     const int64_t pid = idx ? idx[slot] : slot;
     int ist[IS_SIZE];
@@ -330,23 +338,29 @@ round_kernel(int64_t A, const int32_t* __restrict__ idx,
         for (int i = 0; i < SS; i++) st[i] = sp[i];
     }
     double ln[L::SIZE];
-    const double* lp = lin + slot * (int64_t)L::SIZE;
+    if (MODE != 2) {             // the resumed part never reads the record
+        const double* lp = lin + slot * (int64_t)L::SIZE;
 #pragma unroll
-    for (int i = 0; i < L::SIZE; i += 2) {
-        double2 t = *reinterpret_cast<const double2*>(lp + i);
-        ln[i] = t.x;
-        ln[i + 1] = t.y;
+        for (int i = 0; i < L::SIZE; i += 2) {
+            double2 t = *reinterpret_cast<const double2*>(lp + i);
+            ln[i] = t.x;
+            ln[i + 1] = t.y;
+        }
     }
     double sc[N];
 #pragma unroll
     for (int i = 0; i < N; i++) sc[i] = scaling ? scaling[i] : 1.0;
     bool go;
-    if (METHOD == BLSQ_METHOD_TRF)
-        go = trf_round<N>(st, ist, ln, x0 + pid * N, lb + pid * bstride,
-                          ub + pid * bstride, sc, P, first);
-    else
+    if (METHOD == BLSQ_METHOD_TRF) {
+        const int rc = trf_round_impl<N, MODE>(st, ist, ln, x0 + pid * N, lb + pid * bstride,
+                                               ub + pid * bstride, sc, P, first);
+        go = rc == 1;
+        if (MODE == 1 && rc == TRF_DEFER)
+            work[1 + atomicAdd(work, 1)] = (int32_t)slot;
+    } else {
         go = dogbox_round<N>(st, ist, ln, x0 + pid * N, lb + pid * bstride,
                              ub + pid * bstride, sc, P, first);
+    }
     if (SS % 2 == 0) {
 #pragma unroll
         for (int i = 0; i < SS; i += 2)
@@ -426,6 +440,109 @@ __global__ void count_running_kernel(int64_t B,
     if ((threadIdx.x & 31) == 0 && bal) atomicAdd(count, __popc(bal));
 }
 
+
+// ---- ordered compaction of the active set (three small launches) ------------
+// Slot s (problem idx[s], or s) survives when its problem is still running;
+// survivors keep their order.  Each block owns CMP_SLOTS consecutive slots.
+constexpr int CMP_THREADS = 256;
+constexpr int CMP_PER = 4;
+constexpr int CMP_SLOTS = CMP_THREADS * CMP_PER;
+
+__device__ __forceinline__ int compact_local(int64_t A, const int32_t* __restrict__ idx,
+                                             const int32_t* __restrict__ istate,
+                                             int64_t base, bool (&keep)[CMP_PER],
+                                             int64_t (&pid)[CMP_PER], int& block_total) {
+    __shared__ int wsum[CMP_THREADS / 32];
+    int c = 0;
+#pragma unroll
+    for (int j = 0; j < CMP_PER; j++) {
+        const int64_t s = base + (int64_t)threadIdx.x * CMP_PER + j;
+        keep[j] = false;
+        pid[j] = 0;
+        if (s < A) {
+            pid[j] = idx ? idx[s] : s;
+            keep[j] = istate[pid[j] * IS_SIZE + IS_STATUS] == ST_RUNNING;
+        }
+        c += keep[j];
+    }
+    // exclusive scan of c over the block
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int inc = c;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, off);
+        if (lane >= off) inc += t;
+    }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    int before = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < CMP_THREADS / 32; w++) {
+        const int v = wsum[w];
+        if (w < warp) before += v;
+        total += v;
+    }
+    block_total = total;
+    return before + inc - c;
+}
+
+__global__ void __launch_bounds__(CMP_THREADS)
+compact_count_kernel(int64_t A, const int32_t* __restrict__ idx,
+                     const int32_t* __restrict__ istate, int32_t* __restrict__ bsum) {
+    bool keep[CMP_PER];
+    int64_t pid[CMP_PER];
+    int total;
+    compact_local(A, idx, istate, (int64_t)blockIdx.x * CMP_SLOTS, keep, pid, total);
+    if (threadIdx.x == 0) bsum[blockIdx.x] = total;
+}
+
+// exclusive scan of the block totals by one block (serial chunks per thread)
+__global__ void __launch_bounds__(1024)
+compact_scan_kernel(int nblocks, int32_t* __restrict__ bsum) {
+    __shared__ int part[1024];
+    const int per = (nblocks + 1023) / 1024;
+    const int b0 = threadIdx.x * per;
+    int s = 0;
+    for (int k = 0; k < per; k++)
+        if (b0 + k < nblocks) s += bsum[b0 + k];
+    part[threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int t = 0; t < 1024; t++) { const int v = part[t]; part[t] = run; run += v; }
+    }
+    __syncthreads();
+    int run = part[threadIdx.x];
+    for (int k = 0; k < per; k++)
+        if (b0 + k < nblocks) { const int v = bsum[b0 + k]; bsum[b0 + k] = run; run += v; }
+}
+
+__global__ void __launch_bounds__(CMP_THREADS)
+compact_scatter_kernel(int64_t A, const int32_t* __restrict__ idx,
+                       const int32_t* __restrict__ istate, int n,
+                       const int32_t* __restrict__ boff,
+                       const double* __restrict__ Xnew, const double* __restrict__ Xjac,
+                       int32_t* __restrict__ idx_out, int64_t* __restrict__ idx64_out,
+                       double* __restrict__ Xnew_out, double* __restrict__ Xjac_out) {
+    bool keep[CMP_PER];
+    int64_t pid[CMP_PER];
+    int total;
+    const int64_t base = (int64_t)blockIdx.x * CMP_SLOTS;
+    int pos = boff[blockIdx.x] + compact_local(A, idx, istate, base, keep, pid, total);
+#pragma unroll
+    for (int j = 0; j < CMP_PER; j++) {
+        if (!keep[j]) continue;
+        const int64_t s = base + (int64_t)threadIdx.x * CMP_PER + j;
+        idx_out[pos] = (int32_t)pid[j];
+        if (idx64_out) idx64_out[pos] = pid[j];
+        for (int i = 0; i < n; i++) {
+            Xnew_out[(int64_t)pos * n + i] = Xnew[s * n + i];
+            if (Xjac) Xjac_out[(int64_t)pos * n + i] = Xjac[s * n + i];
+        }
+        pos++;
+    }
+}
+
 template <int N, int G, bool MULTI>
 int launch_lin_g(int64_t A, const int32_t* idx, int m, const double* F,
                  const double* J, const PtrList<N>& pl, const double* dx,
@@ -471,15 +588,27 @@ int launch_round(int method, int64_t A, const int32_t* idx, const double* lin,
                  const double* x0, const double* lb, const double* ub,
                  int bstride, const double* scaling, SolveParams P, int first,
                  double* state, int32_t* istate, double* Xnew, double* Xjac,
-                 cudaStream_t s) {
+                 int32_t* work, cudaStream_t s) {
     int64_t blocks = (A + BLSQ_ROUND_THREADS - 1) / BLSQ_ROUND_THREADS;
     if (blocks > 0x7fffffff) return BLSQ_E_UNSUPPORTED;
-    if (method == BLSQ_METHOD_TRF)
-        round_kernel<N, BLSQ_METHOD_TRF><<<(unsigned)blocks, BLSQ_ROUND_THREADS, 0, s>>>(
-            A, idx, lin, x0, lb, ub, bstride, scaling, P, first, state, istate, Xnew, Xjac);
-    else
-        round_kernel<N, BLSQ_METHOD_DOGBOX><<<(unsigned)blocks, BLSQ_ROUND_THREADS, 0, s>>>(
-            A, idx, lin, x0, lb, ub, bstride, scaling, P, first, state, istate, Xnew, Xjac);
+    const unsigned gb = (unsigned)blocks;
+    if (method == BLSQ_METHOD_TRF && work) {
+        cudaError_t e = cudaMemsetAsync(work, 0, sizeof(int32_t), s);
+        if (e != cudaSuccess) return (int)e;
+        round_kernel<N, BLSQ_METHOD_TRF, 1><<<gb, BLSQ_ROUND_THREADS, 0, s>>>(
+            A, idx, lin, x0, lb, ub, bstride, scaling, P, first, state, istate, Xnew, Xjac, work);
+        BLSQ_LAUNCH_CHECK();
+        // the worklist length is only known on the device: full grid, the
+        // blocks past work[0] exit at once
+        round_kernel<N, BLSQ_METHOD_TRF, 2><<<gb, BLSQ_ROUND_THREADS, 0, s>>>(
+            A, idx, lin, x0, lb, ub, bstride, scaling, P, first, state, istate, Xnew, Xjac, work);
+    } else if (method == BLSQ_METHOD_TRF) {
+        round_kernel<N, BLSQ_METHOD_TRF, 0><<<gb, BLSQ_ROUND_THREADS, 0, s>>>(
+            A, idx, lin, x0, lb, ub, bstride, scaling, P, first, state, istate, Xnew, Xjac, work);
+    } else {
+        round_kernel<N, BLSQ_METHOD_DOGBOX, 0><<<gb, BLSQ_ROUND_THREADS, 0, s>>>(
+            A, idx, lin, x0, lb, ub, bstride, scaling, P, first, state, istate, Xnew, Xjac, work);
+    }
     BLSQ_LAUNCH_CHECK();
     return 0;
 }
@@ -576,7 +705,7 @@ int blsq_round_batched(int method, int64_t A, const int32_t* idx, int m, int n,
                        const double* ub, int bstride, const double* scaling,
                        double ftol, double xtol, double gtol, int max_nfev,
                        int first, double* state, int32_t* istate, double* Xnew,
-                       double* Xjac, void* stream) {
+                       double* Xjac, int32_t* work, void* stream) {
     if (A < 0 || !lin || !x0 || !lb || !ub || !state || !istate || !Xnew) return BLSQ_E_BADARG;
     if (method != BLSQ_METHOD_TRF && method != BLSQ_METHOD_DOGBOX) return BLSQ_E_BADARG;
     if (bstride != 0 && bstride != n) return BLSQ_E_BADARG;
@@ -587,7 +716,7 @@ int blsq_round_batched(int method, int64_t A, const int32_t* idx, int m, int n,
     BLSQ_DISPATCH_N(n, {
         return launch_round<N_>(method, A, idx, lin, x0, lb, ub, bstride,
                                 scaling, P, first, state, istate, Xnew, Xjac,
-                                (cudaStream_t)stream);
+                                work, (cudaStream_t)stream);
     });
     return 0;
 }
@@ -614,4 +743,30 @@ int blsq_count_running(int64_t B, const int32_t* idx, const int32_t* istate,
     return 0;
 }
 
+int64_t blsq_compact_work_size(int64_t A) {
+    if (A < 0) return BLSQ_E_BADARG;
+    return (A + CMP_SLOTS - 1) / CMP_SLOTS + 1;
+}
+
+int blsq_compact_batched(int64_t A, const int32_t* idx, const int32_t* istate, int n,
+                         const double* Xnew, const double* Xjac, int32_t* idx_out,
+                         int64_t* idx64_out, double* Xnew_out, double* Xjac_out,
+                         int32_t* work, void* stream) {
+    if (A < 0 || n < 1 || !istate || !Xnew || !idx_out || !Xnew_out || !work) return BLSQ_E_BADARG;
+    if (Xjac && !Xjac_out) return BLSQ_E_BADARG;
+    if (A >= ((int64_t)1 << 31)) return BLSQ_E_UNSUPPORTED;      /* problem ids are int32 */
+    if (A == 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int nblocks = (int)((A + CMP_SLOTS - 1) / CMP_SLOTS);
+    compact_count_kernel<<<nblocks, CMP_THREADS, 0, s>>>(A, idx, istate, work);
+    BLSQ_LAUNCH_CHECK();
+    compact_scan_kernel<<<1, 1024, 0, s>>>(nblocks, work);
+    BLSQ_LAUNCH_CHECK();
+    compact_scatter_kernel<<<nblocks, CMP_THREADS, 0, s>>>(A, idx, istate, n, work, Xnew, Xjac,
+                                                          idx_out, idx64_out, Xnew_out, Xjac_out);
+    BLSQ_LAUNCH_CHECK();
+    return 0;
+}
+
 }  // extern "C"
+

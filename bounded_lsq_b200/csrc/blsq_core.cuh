@@ -326,11 +326,8 @@ BLSQ_HD void jacobi_rows(double* A, double* b) {
 // and Rh = R*diag(d) (packed) for the quadratic-model evaluations
 // (trf.py:69-74,100-102).
 template <int N>
-BLSQ_HD void hat_svd(const double* R, const double* qtf, const double* d,
-                     const double* diag_h, double* Rh, double* s, double* Vt,
-                     double* suf) {
-    double A[N * N];
-    double b[N];
+BLSQ_HD void hat_fold(const double* R, const double* qtf, const double* d,
+                      const double* diag_h, double* Rh, double* A, double* b) {
     BLSQ_UNROLL
     for (int i = 0; i < N; i++) {
         b[i] = qtf[i];
@@ -374,6 +371,11 @@ BLSQ_HD void hat_svd(const double* R, const double* qtf, const double* d,
             bz = fma(-sn, bi, c * bz);
         }
     }
+}
+
+// Jacobi on the folded triangle and extraction of s, Vt, suf (see hat_svd)
+template <int N>
+BLSQ_HD void hat_finish(double* A, double* b, double* s, double* Vt, double* suf) {
     jacobi_rows<N>(A, b);
     BLSQ_UNROLL
     for (int j = 0; j < N; j++) {
@@ -386,6 +388,74 @@ BLSQ_HD void hat_svd(const double* R, const double* qtf, const double* d,
         BLSQ_UNROLL
         for (int i = 0; i < N; i++) Vt[j * N + i] = A[j * N + i] * inv;
     }
+}
+
+template <int N>
+BLSQ_HD void hat_svd(const double* R, const double* qtf, const double* d,
+                     const double* diag_h, double* Rh, double* s, double* Vt,
+                     double* suf) {
+    double A[N * N];
+    double b[N];
+    hat_fold<N>(R, qtf, d, diag_h, Rh, A, b);
+    hat_finish<N>(A, b, s, Vt, suf);
+}
+
+// Gauss-Newton shortcut of solve_lsq_trust_region (trust_region.py:108-117)
+// on the folded triangle A (upper triangular) and b = top of Q'^T f_aug:
+// the reference takes p = -V (uf / s) and returns (p, 0.0) when the matrix has
+// full rank and |p| <= Delta.  Here p = -A^-1 b through the explicit
+// triangular inverse T, and full rank is CERTIFIED by the bound
+// cond(A) <= |A|_F |T|_F (so s_min / s_max > EPS m with a factor 4 to spare).
+// Returns false -- and the caller falls back to the SVD route -- when the
+// certificate fails, the step is longer than Delta, or |p| is within 1e-9 of
+// Delta (so that the accept / Levenberg-Marquardt decision is always taken by
+// the reference's own arithmetic).  ~95 % of the C2 trust-region solves are
+// Gauss-Newton steps (oracle count), none of them needs the Jacobi sweeps.
+template <int N>
+BLSQ_HD bool gn_shortcut(const double* A, const double* b, int m, double Delta,
+                         double* p_h) {
+    if (m < N) return false;
+    double T[N * N];
+    double fa = 0.0, ft = 0.0;
+    BLSQ_UNROLL
+    for (int i = 0; i < N; i++) {
+        const double aii = A[i * N + i];
+        if (!(aii != 0.0)) return false;
+        T[i * N + i] = 1.0 / aii;
+    }
+    BLSQ_UNROLL
+    for (int i = 0; i < N; i++) {
+        BLSQ_UNROLL
+        for (int j = 0; j < N; j++) {
+            if (j < i) continue;
+            fa = fma(A[i * N + j], A[i * N + j], fa);
+            if (j > i) {
+                double acc = 0.0;
+                BLSQ_UNROLL
+                for (int k = 0; k < N; k++) {
+                    if (k < i || k >= j) continue;
+                    acc = fma(T[i * N + k], A[k * N + j], acc);
+                }
+                T[i * N + j] = -acc * T[j * N + j];
+            }
+            ft = fma(T[i * N + j], T[i * N + j], ft);
+        }
+    }
+    const double em = EPS * m;
+    if (!(fa * ft * (em * em) < 0.0625)) return false;     // also rejects NaN / inf
+    double nn = 0.0;
+    BLSQ_UNROLL
+    for (int i = 0; i < N; i++) {
+        double acc = 0.0;
+        BLSQ_UNROLL
+        for (int j = 0; j < N; j++) {
+            if (j < i) continue;
+            acc = fma(T[i * N + j], b[j], acc);
+        }
+        p_h[i] = -acc;
+        nn = fma(acc, acc, nn);
+    }
+    return sqrt(nn) <= Delta * (1.0 - 1e-9);
 }
 
 // ---------------------------------------------------------------------------
@@ -498,15 +568,25 @@ enum { IS_STATUS = 0, IS_NFEV = 1, IS_NJEV = 2, IS_ONB = 3, IS_MARKS = 4,
 // One TRF round for one problem.  `lin` is the linearisation at the trial
 // point XNEW (or at the strictly feasible start when first != 0).
 // Returns true when a new trial point was written to st[XNEW].
-template <int N>
-BLSQ_HD bool trf_round(double* st, int* ist, const double* lin,
-                       const double* x0, const double* lb, const double* ub,
-                       const double* scaling, const SolveParams& P, int first) {
+// MODE 0: the whole round, SVD route (one kernel).  MODE 1: the whole round
+// with the Gauss-Newton shortcut; returns TRF_DEFER (state updated, no trial
+// written) when the problem needs the SVD route.  MODE 2: resume a deferred
+// problem: skip the judge / accept part (already done by MODE 1; `lin` is not
+// read) and propose through the SVD.  Returns 0 (finished / no trial), 1 (new
+// trial in st[XNEW]) or TRF_DEFER.
+enum { TRF_DEFER = 2 };
+
+template <int N, int MODE>
+BLSQ_HD int trf_round_impl(double* st, int* ist, const double* lin,
+                           const double* x0, const double* lb, const double* ub,
+                           const double* scaling, const SolveParams& P, int first) {
     typedef TrfState<N> S;
     typedef LinRec<N> L;
     int status = ST_RUNNING;     // pending status set by the inner loop
-    bool adopt;
-    if (first) {
+    bool adopt = false;
+    if (MODE == 2) {
+        first = 0;               // scale / Delta / alpha are in the state already
+    } else if (first) {
         // trf.py:201-235
         ist[IS_NFEV] = 1;
         ist[IS_NJEV] = 0;
@@ -631,8 +711,7 @@ BLSQ_HD bool trf_round(double* st, int* ist, const double* lin,
         return false;
     }
 
-    double Rh[S::NT], s[N], Vt[N * N], suf[N];
-    hat_svd<N>(st + S::R, st + S::QTF, d, diag_h, Rh, s, Vt, suf);
+    double Rh[S::NT];
     double theta = 1.0 - g_norm;
     if (theta < 0.995) theta = 0.995;
 
@@ -640,7 +719,18 @@ BLSQ_HD bool trf_round(double* st, int* ist, const double* lin,
     double Delta = st[S::DELTA];
     double alpha = st[S::ALPHA];
     double p_h[N], p[N];
-    solve_lsq_trust_region<N>(P.m, suf, s, Vt, Delta, alpha, p_h);
+    {
+        double A[N * N], b[N];
+        hat_fold<N>(st + S::R, st + S::QTF, d, diag_h, Rh, A, b);
+        if (MODE == 1) {
+            if (!gn_shortcut<N>(A, b, P.m, Delta, p_h)) return TRF_DEFER;
+            alpha = 0.0;                           // trust_region.py:117
+        } else {
+            double s[N], Vt[N * N], suf[N];
+            hat_finish<N>(A, b, s, Vt, suf);
+            solve_lsq_trust_region<N>(P.m, suf, s, Vt, Delta, alpha, p_h);
+        }
+    }
     st[S::ALPHA] = alpha;
     BLSQ_UNROLL
     for (int i = 0; i < N; i++) p[i] = d[i] * p_h[i];
@@ -728,6 +818,18 @@ BLSQ_HD bool trf_round(double* st, int* ist, const double* lin,
     st[S::NSTEPH] = norm2<N>(step_h);
     st[S::NSTEP] = norm2<N>(step);
     return true;
+}
+
+// One TRF round the way the two-kernel device path runs it: Gauss-Newton
+// shortcut first, SVD route for the problems that need it.
+template <int N>
+BLSQ_HD bool trf_round(double* st, int* ist, const double* lin,
+                       const double* x0, const double* lb, const double* ub,
+                       const double* scaling, const SolveParams& P, int first) {
+    int rc = trf_round_impl<N, 1>(st, ist, lin, x0, lb, ub, scaling, P, first);
+    if (rc == TRF_DEFER)
+        rc = trf_round_impl<N, 2>(st, ist, lin, x0, lb, ub, scaling, P, first);
+    return rc == 1;
 }
 
 // ---------------------------------------------------------------------------

@@ -54,9 +54,8 @@ gausspeak_kernel(int64_t A, const int64_t* __restrict__ idx, int m,
 // first k columns, so the residual kernel reads A from there:
 //   f = J[:, :k] x[:k] + x_k e^{-x_{k+1} t} + x_{k+2} e^{-x_{k+3} t} - y
 // A warp takes 32 consecutive rows: each half warp streams 16 of them (16
-// lanes per row, 16-byte loads, all rows of the tile in flight together, one
-// transposing butterfly so that lane i keeps the sum of row i), then all 32
-// lanes evaluate the exponentials of their own row at once.
+// lanes per row, 16-byte loads, shuffle reduction, lane i keeps the sum of row
+// i), then all 32 lanes evaluate the exponentials of their own row at once.
 __global__ void __launch_bounds__(256)
 linexp_fun_kernel(int64_t m, int n, const double* __restrict__ J,
                   const double* __restrict__ t, const double* __restrict__ y,
@@ -70,36 +69,23 @@ linexp_fun_kernel(int64_t m, int n, const double* __restrict__ J,
     const int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const double xk = xs[k], xk1 = xs[k + 1], xk2 = xs[k + 2], xk3 = xs[k + 3];
     for (int64_t base = warp * 32; base < m; base += nwarp * 32) {
-        // Each half warp owns 16 rows; lane l16 accumulates its column slice of
-        // ALL 16 rows (every load of the tile is in flight at once), then a
-        // transposing butterfly (8 + 4 + 2 + 1 exchanges instead of 16 x 4)
-        // leaves the total of row l16 on lane l16.
-        double s[16];
-#pragma unroll
-        for (int it = 0; it < 16; it++) s[it] = 0.0;
-        const int64_t r0 = base + half * 16;
-        for (int c = 2 * l16; c < k; c += 32) {
-            const double x0 = xs[c], x1 = xs[c + 1];
-#pragma unroll
-            for (int it = 0; it < 16; it++) {
-                if (r0 + it < m) {
-                    const double2 a = __ldcs(reinterpret_cast<const double2*>(J + (r0 + it) * n + c));
-                    s[it] = fma(a.x, x0, s[it]);
-                    s[it] = fma(a.y, x1, s[it]);
+        double mine = 0.0;
+#pragma unroll 4
+        for (int it = 0; it < 16; it++) {
+            const int64_t r = base + half * 16 + it;
+            double s = 0.0;
+            if (r < m) {
+                const double* row = J + r * n;
+                for (int c = 2 * l16; c < k; c += 32) {
+                    const double2 a = __ldcs(reinterpret_cast<const double2*>(row + c));
+                    s = fma(a.x, xs[c], s);
+                    s = fma(a.y, xs[c + 1], s);
                 }
             }
-        }
 #pragma unroll
-        for (int off = 8; off > 0; off >>= 1) {
-            const bool up = (l16 & off) != 0;
-#pragma unroll
-            for (int i = 0; i < off; i++) {
-                const double send = up ? s[i] : s[i + off];
-                const double keep = up ? s[i + off] : s[i];
-                s[i] = keep + __shfl_xor_sync(0xffffffffu, send, off, 16);
-            }
+            for (int off = 8; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off, 16);
+            if (l16 == it) mine = s;
         }
-        const double mine = s[0];
         const int64_t r = base + lane;
         if (r < m) {
             const double tr = t[r];

@@ -140,9 +140,17 @@ def least_squares_batched(fun, x0, jac='2-point', bounds=(-float('inf'), float('
     """
     lib = _lib if _lib is not None else L.get_lib()
     _validate_common(method, bounds, jac)
+    options = dict(options)
     if not isinstance(x0, torch.Tensor):
         dev = _default_device() if lib.requires_cuda else torch.device("cpu")
         x0 = torch.as_tensor(x0, dtype=torch.float64, device=dev)
+    elif lib.requires_cuda and not x0.is_cuda:
+        # HOST inputs (x0 and the PerProblem data on the CPU, ideally pinned):
+        # they are streamed to the device in chunks and the first rounds of
+        # each chunk overlap the transfer of the next one
+        x0, args, kwargs, plan = _stage_host_inputs(x0, args, kwargs, options)
+        if plan is not None and "trace" not in options:
+            options["prologue"] = plan
     x0 = x0.to(torch.float64).contiguous()
     if x0.dim() != 2:
         raise ValueError("batched `x0` must be (B, n).")
@@ -172,6 +180,53 @@ def least_squares_batched(fun, x0, jac='2-point', bounds=(-float('inf'), float('
     res.message = TERMINATION_MESSAGES
     res.success = res.status > 0
     return res
+
+
+_COPY_STREAM = {}
+
+
+def _stage_host_inputs(x0, args, kwargs, options):
+    """Device copies of host-resident batched inputs.  x0 (small) is copied at
+    once; every CPU ``PerProblem`` tensor is copied in ``h2d_chunks`` chunks
+    of problems on a side stream, one event per chunk.  Returns the device x0,
+    the rewritten args/kwargs and the [(c0, c1, event)] plan for
+    ``solve_batched(prologue=...)`` (None if there is nothing to stream)."""
+    dev = options.pop("device", None) or _default_device()
+    dev = torch.device(dev)
+    nch = int(options.pop("h2d_chunks", 4))
+    B = x0.shape[0]
+    x0d = x0.to(dev, non_blocking=True)
+    host = [v for v in list(args) + list(dict(kwargs).values())
+            if isinstance(v, PerProblem) and not v.tensor.is_cuda]
+    if not host:
+        return x0d, args, kwargs, None
+    for v in host:
+        if v.tensor.shape[0] != B:
+            raise ValueError("PerProblem data must have leading dimension B.")
+    nch = max(1, min(nch, B // 65536))
+    step = -(-B // nch)
+    main = torch.cuda.current_stream(dev)
+    copy = _COPY_STREAM.get(dev)
+    if copy is None:
+        copy = _COPY_STREAM[dev] = torch.cuda.Stream(dev)
+    bufs = {id(v): torch.empty(v.tensor.shape, dtype=v.tensor.dtype, device=dev)
+            for v in host}
+    copy.wait_stream(main)                  # the buffers were allocated on main
+    plan = []
+    with torch.cuda.stream(copy):
+        for c0 in range(0, B, step):
+            c1 = min(B, c0 + step)
+            for v in host:
+                bufs[id(v)][c0:c1].copy_(v.tensor[c0:c1], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy)
+            plan.append((c0, c1, ev))
+
+    def swap(v):
+        return PerProblem(bufs[id(v)]) if id(v) in bufs else v
+    args = tuple(swap(v) for v in args)
+    kwargs = {k: swap(v) for k, v in dict(kwargs).items()}
+    return x0d, args, kwargs, plan
 
 
 def _single_callbacks(fun, jac, args, kwargs, dev):

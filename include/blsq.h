@@ -145,13 +145,18 @@ int blsq_linearise_batched(int64_t A, const int32_t* idx, int m, int n,
  * evaluated at: for dogbox that is the trial with the coordinates that hit a
  * bound snapped onto it (dogbox.py:256-261 -- f is taken at x_new, J at the
  * snapped x); for TRF it equals Xnew.
- * scaling: n doubles (shared) or null for scaling='jac'. */
+ * scaling: n doubles (shared) or null for scaling='jac'.
+ * work (nullable, A + 1 int32): with it the TRF round runs as two kernels --
+ * every problem takes the Gauss-Newton shortcut of solve_lsq_trust_region
+ * (trust_region.py:108-117: full rank certified, |p| <= Delta; ~95 % of the
+ * solves) and the rest are collected in `work` and finished through the SVD
+ * route with dense warps.  Without it (or for dogbox): one kernel. */
 int blsq_round_batched(int method, int64_t A, const int32_t* idx, int m, int n,
                        const double* lin, const double* x0, const double* lb,
                        const double* ub, int bstride, const double* scaling,
                        double ftol, double xtol, double gtol, int max_nfev,
                        int first, double* state, int32_t* istate, double* Xnew,
-                       double* Xjac, void* stream);
+                       double* Xjac, int32_t* work, void* stream);
 
 /* dogbox.py:152-154,254: on_bound as the reference's int array (B x n) */
 int blsq_dogbox_on_bound(int64_t B, int n, const int32_t* istate,
@@ -161,6 +166,18 @@ int blsq_dogbox_on_bound(int64_t B, int n, const int32_t* istate,
  * still running (device int32) */
 int blsq_count_running(int64_t A, const int32_t* idx, const int32_t* istate,
                        int32_t* count, void* stream);
+
+/* Ordered compaction of the active set (host logic of the lock-step driver;
+ * no reference counterpart: the reference solves one problem per call).  Slots
+ * whose problem is still running keep their order: idx_out[k] (int32) and
+ * idx64_out[k] (nullable, for torch gathers) = problem id of the k-th
+ * survivor, Xnew_out / Xjac_out (k, n) its trial points (Xjac nullable).  The
+ * outputs must not alias the inputs.  work: blsq_compact_work_size(A) int32. */
+int64_t blsq_compact_work_size(int64_t A);
+int blsq_compact_batched(int64_t A, const int32_t* idx, const int32_t* istate, int n,
+                         const double* Xnew, const double* Xjac, int32_t* idx_out,
+                         int64_t* idx64_out, double* Xnew_out, double* Xjac_out,
+                         int32_t* work, void* stream);
 
 
 /* ---- tall mode: one problem, m_local rows on this rank, n even, n <= 256 --

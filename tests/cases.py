@@ -262,6 +262,40 @@ def check_graph_tail_invariance(lib, dev):
     return out
 
 
+def check_prologue_invariance(lib, dev, host_inputs=False):
+    """Streaming start (each chunk of problems runs its first rounds alone,
+    then the batch carries on in lock step): same bits as the plain solve.
+    With host_inputs the data is handed over as pinned CPU tensors and the
+    front end stages it chunk by chunk."""
+    for cfg, method, jac in (("c2", "trf", "exact"), ("c3", "dogbox", "2-point"),
+                             ("c2", "dogbox", "exact")):
+        model = MODELS[cfg]()
+        B = 1500 if not host_inputs else 200000
+        _, y = model.make_data(min(B, 4096), seed=5)
+        y = np.tile(y, (-(-B // y.shape[0]), 1))[:B].copy()
+        yt = T(y, dev)
+        X0 = T(np.tile(model.x0, (B, 1)), dev)
+        j = model.jac_t if jac == "exact" else jac
+        lbt, ubt = T(model.lb, dev), T(model.ub, dev)
+
+        def solve(x0=X0, yy=yt, **opts):
+            return least_squares_batched(
+                model.fun_t, x0, jac=j, bounds=(lbt, ubt), method=method,
+                args=(PerProblem(yy),), options=opts, _lib=lib)
+
+        base = solve()
+        runs = [solve(prologue=[(0, 400, None), (400, 1001, None), (1001, B, None)],
+                      prologue_rounds=3),
+                solve(prologue=[(0, B, None)], prologue_rounds=50)]
+        if host_inputs:
+            runs.append(solve(x0=X0.cpu().pin_memory(), yy=yt.cpu().pin_memory(),
+                              h2d_chunks=3, prologue_rounds=4))
+        for k, r in enumerate(runs):
+            for fld in ("x", "obj_value", "status", "nfev", "njev", "active_mask"):
+                assert bits(getattr(r, fld).cpu().numpy(),
+                            getattr(base, fld).cpu().numpy()), (cfg, method, k, fld)
+
+
 def check_per_problem_bounds(lib, dev):
     """(B, n) bounds give the same answers as shared (n,) bounds."""
     model = ExpDecay2()

@@ -271,7 +271,7 @@ int blsq_round_batched(int method, int64_t A, const int32_t* idx, int m, int n,
                        const double* ub, int bs, const double* scaling,
                        double ftol, double xtol, double gtol, int max_nfev,
                        int first, double* state, int32_t* istate, double* Xnew,
-                       double* Xjac, void*) {
+                       double* Xjac, int32_t* /*work*/, void*) {
     SolveParams P;
     P.ftol = ftol; P.xtol = xtol; P.gtol = gtol;
     P.max_nfev = max_nfev; P.m = m; P.jac_scaling = scaling ? 0 : 1;
@@ -330,6 +330,27 @@ int blsq_count_running(int64_t B, const int32_t* idx, const int32_t* istate,
     for (int64_t b = 0; b < B; b++)
         c += istate[(idx ? idx[b] : b) * IS_SIZE + IS_STATUS] == ST_RUNNING;
     *count = c;
+    return 0;
+}
+
+int64_t blsq_compact_work_size(int64_t A) { return A < 0 ? BLSQ_E_BADARG : A / 1024 + 2; }
+
+int blsq_compact_batched(int64_t A, const int32_t* idx, const int32_t* istate, int n,
+                         const double* Xnew, const double* Xjac, int32_t* idx_out,
+                         int64_t* idx64_out, double* Xnew_out, double* Xjac_out,
+                         int32_t*, void*) {
+    int64_t pos = 0;
+    for (int64_t s = 0; s < A; s++) {
+        const int64_t pid = idx ? idx[s] : s;
+        if (istate[pid * IS_SIZE + IS_STATUS] != ST_RUNNING) continue;
+        idx_out[pos] = (int32_t)pid;
+        if (idx64_out) idx64_out[pos] = pid;
+        for (int i = 0; i < n; i++) {
+            Xnew_out[pos * n + i] = Xnew[s * n + i];
+            if (Xjac) Xjac_out[pos * n + i] = Xjac[s * n + i];
+        }
+        pos++;
+    }
     return 0;
 }
 

@@ -43,6 +43,10 @@ def test_compaction_invariance(lib):
     cases.check_compaction_invariance(lib, DEV)
 
 
+def test_prologue_invariance(lib):
+    cases.check_prologue_invariance(lib, DEV)
+
+
 def test_per_problem_bounds(lib):
     cases.check_per_problem_bounds(lib, DEV)
 

@@ -50,6 +50,10 @@ def test_graph_tail_invariance(lib, dev):
     print(cases.check_graph_tail_invariance(lib, dev))
 
 
+def test_prologue_invariance(lib, dev):
+    cases.check_prologue_invariance(lib, dev, host_inputs=True)
+
+
 def test_per_problem_bounds(lib, dev):
     cases.check_per_problem_bounds(lib, dev)
 

@@ -59,6 +59,8 @@ def main():
         Fp = [model.fun_t(Xp[i], y).contiguous() for i in range(n)]
         arr = (C.c_void_p * n)(*[t.data_ptr() for t in Fp])
         mode, plist, dxp, J = 1, C.cast(arr, C.c_void_p), dx.data_ptr(), None
+    RW = torch.empty(B + 1, dtype=torch.int32, device=dev).data_ptr() \
+        if os.environ.get('BLSQ_TRF_TWO_KERNELS', '1') != '0' else None
     torch.cuda.synchronize()
 
     def t_lin():
@@ -71,7 +73,7 @@ def main():
         lib.call("blsq_round_batched", method, B, None, m, n, lin.data_ptr(),
                  X0.data_ptr(), lb.data_ptr(), ub.data_ptr(), 0, sc.data_ptr(),
                  1.5e-8, 1.5e-8, 1.5e-8, 100 * n, 1, state.data_ptr(),
-                 istate.data_ptr(), Xnew.data_ptr(), None, st)
+                 istate.data_ptr(), Xnew.data_ptr(), None, RW, st)
 
     def timeit(fn, pre=None):
         ts = []
@@ -95,7 +97,7 @@ def main():
         lib.call("blsq_round_batched", method, B, None, m, n, lin.data_ptr(),
                  X0.data_ptr(), lb.data_ptr(), ub.data_ptr(), 0, sc.data_ptr(),
                  1.5e-8, 1.5e-8, 1.5e-8, 100 * n, 1, state.data_ptr(),
-                 istate.data_ptr(), Xnew.data_ptr(), None, st)
+                 istate.data_ptr(), Xnew.data_ptr(), None, RW, st)
 
     def reset():
         istate[:, 0].fill_(-1)
