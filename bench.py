@@ -680,6 +680,11 @@ def main():
         "algorithmic_bytes_per_problem": lin.get("bytes_per_problem"),
         "avg_launch_ms": lin.get("avg_ms"), "launches": lin.get("launches"),
         "share_of_kernel_time": lin.get("share"),
+        # the same kernel on the launches that still see the whole batch
+        # (the average above includes ~100 latency-sized tail launches)
+        "full_batch_launches": dict(
+            lin.get("full_batch", {}),
+            frac=(lin["full_batch"]["gbs"] / peak) if lin.get("full_batch") else None),
         "round_kernel": {"avg_launch_ms": rnd.get("avg_ms"),
                          "share_of_kernel_time": rnd.get("share"),
                          "gbs": rnd.get("gbs")},

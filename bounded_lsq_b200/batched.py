@@ -188,6 +188,9 @@ def solve_batched(lib, method, fun, jac, X0, lb, ub, ftol, xtol, gtol,
     if method == "trf" and os.environ.get("BLSQ_TRF_TWO_KERNELS", "1") != "0":
         rwork = torch.empty(B + 1, dtype=torch.int32, device=dev)
     rwork_ptr = None if rwork is None else rwork.data_ptr()
+    # latency-sized rounds are faster as ONE kernel (measured: the second
+    # launch costs the tail what the shortcut saves the bulk)
+    TWO_KERNELS_ABOVE = 32768
     if fd:
         Xp = torch.empty((npts, B, n), dtype=f64, device=dev)
         dx = torch.empty((B, 2 * n if fd3 else n), dtype=f64, device=dev)
@@ -290,11 +293,12 @@ def solve_batched(lib, method, fun, jac, X0, lb, ub, ftol, xtol, gtol,
         lib.call("blsq_round_batched", meth, A, ip, m, n, p_lin,
                  p_x0, p_lb, p_ub, bstride, sc_ptr,
                  float(ftol), float(xtol), float(gtol), max_nfev, first,
-                 p_st, p_ist, p_xn, p_xj, rwork_ptr, stream)
+                 p_st, p_ist, p_xn, p_xj,
+                 rwork_ptr if A >= TWO_KERNELS_ABOVE else None, stream)
         tock("round", t0, nrun)
         if timers is not None:
             timers["shape"] = (n, m, LS, S)
-        launches += 2 if rwork is None else 3
+        launches += 2 if (rwork is None or A < TWO_KERNELS_ABOVE) else 3
 
     def count_running(A, idx32):
         nonlocal launches
@@ -334,7 +338,10 @@ def solve_batched(lib, method, fun, jac, X0, lb, ub, ftol, xtol, gtol,
         side.wait_stream(cur)
         try:
             with torch.cuda.stream(side):
-                g.capture_begin(pool=_graph_pool(dev))
+                # thread_local: other threads (NCCL watchdog, NVML sampler)
+                # keep making CUDA calls during the capture
+                g.capture_begin(pool=_graph_pool(dev),
+                                capture_error_mode="thread_local")
                 if dbg:
                     tt.append(time.perf_counter())
                 try:
@@ -351,6 +358,14 @@ def solve_batched(lib, method, fun, jac, X0, lb, ub, ftol, xtol, gtol,
                 tt.append(time.perf_counter())
         except Exception as e:                 # noqa: BLE001
             torch.cuda.synchronize(dev)
+            # a capture that died half way leaves the allocator routing this
+            # stream to the shared pool: stop that and start a fresh pool
+            try:
+                torch._C._cuda_endAllocateToPool(dev.index or 0, _graph_pool(dev))
+            except Exception:                  # noqa: BLE001
+                pass
+            _POOL.pop(dev, None)
+            _LAST_GRAPH.pop(dev, None)
             launches = l1
             _NOT_CAPTURABLE.add(_cb_key(fun, jac))
             warnings.warn("bounded_lsq_b200: the callbacks could not be "
@@ -490,6 +505,13 @@ def summarize_timers(timers):
                              avg_ms=tot[kind] / len(ms),
                              gbs=byts / (tot[kind] * 1e-3) / 1e9,
                              bytes_per_problem=per[kind])
+            # the launches that still see the whole batch (bandwidth sized)
+            rmax = max(r for _, _, r in ev)
+            full = [t for t, (_, _, r) in zip(ms, ev) if r == rmax]
+            out[kind]["full_batch"] = dict(
+                launches=len(full), running=rmax,
+                avg_ms=sum(full) / len(full),
+                gbs=rmax * per[kind] * len(full) / (sum(full) * 1e-3) / 1e9)
     kt = tot["linearise"] + tot["round"]
     for kind in ("linearise", "round"):
         if kind in out:

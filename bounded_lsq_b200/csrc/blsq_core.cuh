@@ -568,9 +568,9 @@ enum { IS_STATUS = 0, IS_NFEV = 1, IS_NJEV = 2, IS_ONB = 3, IS_MARKS = 4,
 // One TRF round for one problem.  `lin` is the linearisation at the trial
 // point XNEW (or at the strictly feasible start when first != 0).
 // Returns true when a new trial point was written to st[XNEW].
-// MODE 0: the whole round, SVD route (one kernel).  MODE 1: the whole round
-// with the Gauss-Newton shortcut; returns TRF_DEFER (state updated, no trial
-// written) when the problem needs the SVD route.  MODE 2: resume a deferred
+// MODE 0: the whole round in one piece: Gauss-Newton shortcut, else the SVD
+// route.  MODE 1: the same, but returns TRF_DEFER (state updated, no trial
+// written) instead of entering the SVD route.  MODE 2: resume a deferred
 // problem: skip the judge / accept part (already done by MODE 1; `lin` is not
 // read) and propose through the SVD.  Returns 0 (finished / no trial), 1 (new
 // trial in st[XNEW]) or TRF_DEFER.
@@ -722,9 +722,12 @@ BLSQ_HD int trf_round_impl(double* st, int* ist, const double* lin,
     {
         double A[N * N], b[N];
         hat_fold<N>(st + S::R, st + S::QTF, d, diag_h, Rh, A, b);
-        if (MODE == 1) {
-            if (!gn_shortcut<N>(A, b, P.m, Delta, p_h)) return TRF_DEFER;
+        // every mode takes the same decision with the same arithmetic, so the
+        // result does not depend on how the driver splits the work
+        if (MODE != 2 && gn_shortcut<N>(A, b, P.m, Delta, p_h)) {
             alpha = 0.0;                           // trust_region.py:117
+        } else if (MODE == 1) {
+            return TRF_DEFER;
         } else {
             double s[N], Vt[N * N], suf[N];
             hat_finish<N>(A, b, s, Vt, suf);
@@ -826,6 +829,7 @@ template <int N>
 BLSQ_HD bool trf_round(double* st, int* ist, const double* lin,
                        const double* x0, const double* lb, const double* ub,
                        const double* scaling, const SolveParams& P, int first) {
+    // host emulation: exercise the deferred path the way the two kernels do
     int rc = trf_round_impl<N, 1>(st, ist, lin, x0, lb, ub, scaling, P, first);
     if (rc == TRF_DEFER)
         rc = trf_round_impl<N, 2>(st, ist, lin, x0, lb, ub, scaling, P, first);

@@ -56,6 +56,17 @@ gausspeak_kernel(int64_t A, const int64_t* __restrict__ idx, int m,
 // A warp takes 32 consecutive rows: each half warp streams 16 of them (16
 // lanes per row, 16-byte loads, shuffle reduction, lane i keeps the sum of row
 // i), then all 32 lanes evaluate the exponentials of their own row at once.
+#ifndef BLSQ_FUN_UNROLL
+#define BLSQ_FUN_UNROLL 4
+#endif
+constexpr int FUN_UNROLL = BLSQ_FUN_UNROLL;
+#ifndef BLSQ_FUN_VARIANT
+#define BLSQ_FUN_VARIANT 0
+#endif
+#ifndef BLSQ_FUN_RB
+#define BLSQ_FUN_RB 8
+#endif
+
 __global__ void __launch_bounds__(256)
 linexp_fun_kernel(int64_t m, int n, const double* __restrict__ J,
                   const double* __restrict__ t, const double* __restrict__ y,
@@ -69,8 +80,56 @@ linexp_fun_kernel(int64_t m, int n, const double* __restrict__ J,
     const int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const double xk = xs[k], xk1 = xs[k + 1], xk2 = xs[k + 2], xk3 = xs[k + 3];
     for (int64_t base = warp * 32; base < m; base += nwarp * 32) {
+#if BLSQ_FUN_VARIANT == 1
+        // RB rows of this half warp per batch: all their loads are issued
+        // before the first reduction (rows past m are clamped, their sums are
+        // never stored), then one transposing butterfly per batch
+        constexpr int RB = BLSQ_FUN_RB;
         double mine = 0.0;
-#pragma unroll 4
+        const int64_t r0 = base + half * 16;
+#pragma unroll
+        for (int b0 = 0; b0 < 16; b0 += RB) {
+            double s[RB];
+#pragma unroll
+            for (int i = 0; i < RB; i++) s[i] = 0.0;
+            for (int c = 2 * l16; c < k; c += 32) {
+                const double x0 = xs[c], x1 = xs[c + 1];
+                double2 a[RB];
+#pragma unroll
+                for (int i = 0; i < RB; i++) {
+                    int64_t r = r0 + b0 + i;
+                    r = r < m ? r : m - 1;
+                    a[i] = __ldcs(reinterpret_cast<const double2*>(J + r * n + c));
+                }
+#pragma unroll
+                for (int i = 0; i < RB; i++) {
+                    s[i] = fma(a[i].x, x0, s[i]);
+                    s[i] = fma(a[i].y, x1, s[i]);
+                }
+            }
+            // butterfly over the 16 lanes: the RB sums end up spread over the
+            // lanes (lane j of every group of RB lanes holds row b0 + j)
+#pragma unroll
+            for (int off = 8; off >= RB; off >>= 1) {
+#pragma unroll
+                for (int i = 0; i < RB; i++) s[i] += __shfl_xor_sync(0xffffffffu, s[i], off, 16);
+            }
+#pragma unroll
+            for (int off = RB / 2; off > 0; off >>= 1) {
+                const bool up = (l16 & off) != 0;
+#pragma unroll
+                for (int i = 0; i < off; i++) {
+                    const double send = up ? s[i] : s[i + off];
+                    const double keep = up ? s[i + off] : s[i];
+                    s[i] = keep + __shfl_xor_sync(0xffffffffu, send, off, 16);
+                }
+            }
+            // lane l16 holds row b0 + (l16 % RB); lane (b0 + j) needs row b0 + j
+            if ((l16 & ~(RB - 1)) == b0) mine = s[0];
+        }
+#else
+        double mine = 0.0;
+#pragma unroll FUN_UNROLL
         for (int it = 0; it < 16; it++) {
             const int64_t r = base + half * 16 + it;
             double s = 0.0;
@@ -86,6 +145,7 @@ linexp_fun_kernel(int64_t m, int n, const double* __restrict__ J,
             for (int off = 8; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off, 16);
             if (l16 == it) mine = s;
         }
+#endif
         const int64_t r = base + lane;
         if (r < m) {
             const double tr = t[r];
