@@ -57,14 +57,14 @@ gausspeak_kernel(int64_t A, const int64_t* __restrict__ idx, int m,
 // lanes per row, 16-byte loads, shuffle reduction, lane i keeps the sum of row
 // i), then all 32 lanes evaluate the exponentials of their own row at once.
 #ifndef BLSQ_FUN_UNROLL
-#define BLSQ_FUN_UNROLL 4
+#define BLSQ_FUN_UNROLL 16
 #endif
 constexpr int FUN_UNROLL = BLSQ_FUN_UNROLL;
 #ifndef BLSQ_FUN_VARIANT
-#define BLSQ_FUN_VARIANT 0
+#define BLSQ_FUN_VARIANT 1
 #endif
 #ifndef BLSQ_FUN_RB
-#define BLSQ_FUN_RB 8
+#define BLSQ_FUN_RB 4
 #endif
 
 __global__ void __launch_bounds__(256)

@@ -34,8 +34,10 @@ using namespace blsq;
 
 // ---- state records -----------------------------------------------------------
 enum { TS_OBJ = 0, TS_DELTA, TS_ALPHA, TS_PRED, TS_CORR, TS_NSTEPH, TS_NSTEP, TS_GNORM,
+       TS_GNSTEP,        // |p_gn| of the cached Gauss-Newton step (TI_GN = 1)
        TS_NSCAL = 16 };
 enum { TI_STATUS = 0, TI_NFEV, TI_NJEV, TI_ACCEPT, TI_PENDING, TI_TRHIT, TI_SWEEPS,
+       TI_GN,            // 1: the state holds the Gauss-Newton step (in SUF), no SVD yet
        TI_NSCAL = 8 };
 
 struct TallLayout {
@@ -459,8 +461,7 @@ BLSQ_HD void tall_fold(const Blk& B, double* A, double* b, const double* diag_h,
 // Factorisation of the hat-space augmented matrix (trf.py:264-274) from the
 // triangle: A = R diag(d) with diag(sqrt(diag_h)) folded in, then Jacobi.
 // Outputs (global state): S, SUF = S * (U^T f_aug), VT (row j = v_j).
-BLSQ_HD int tall_hat_svd(const Blk& B, const double* R, const TallWork& W, double* A,
-                         double* S, double* SUF, double* VT) {
+BLSQ_HD void tall_hat_fold(const Blk& B, const double* R, const TallWork& W, double* A) {
     const int n = W.n;
     for (int e = B.tid; e < n * n; e += B.nt) {
         const int i = e / n, j = e % n;
@@ -469,6 +470,11 @@ BLSQ_HD int tall_hat_svd(const Blk& B, const double* R, const TallWork& W, doubl
     for (int i = B.tid; i < n; i += B.nt) W.b[i] = W.qtf[i];
     B.sync();
     tall_fold(B, A, W.b, W.diag_h, n, W.rowbuf, W.prog, W.flags);
+}
+
+BLSQ_HD int tall_hat_finish(const Blk& B, const TallWork& W, double* A, double* S, double* SUF,
+                            double* VT) {
+    const int n = W.n;
     const int sweeps = tall_jacobi(B, A, W.b, n);
     for (int j = B.warp; j < n; j += B.nwarps) {
         double nn = 0.0;
@@ -481,6 +487,64 @@ BLSQ_HD int tall_hat_svd(const Blk& B, const double* R, const TallWork& W, doubl
     }
     B.sync();
     return sweeps;
+}
+
+BLSQ_HD int tall_hat_svd(const Blk& B, const double* R, const TallWork& W, double* A,
+                         double* S, double* SUF, double* VT) {
+    tall_hat_fold(B, R, W, A);
+    return tall_hat_finish(B, W, A, S, SUF, VT);
+}
+
+// Gauss-Newton shortcut of solve_lsq_trust_region (trust_region.py:108-117) on
+// the folded triangle A and b (see gn_shortcut in blsq_core.cuh): full rank is
+// certified by cond(A) <= |A|_F |A^-1|_F with a factor 4 to spare against
+// EPS m, the step is p = -A^-1 b.  Every warp back-substitutes whole columns
+// of the identity (only their squared norms are kept) and one extra right-hand
+// side, b; row i of a solve is a lane-parallel dot product over the part of the
+// solution that exists already.  Returns true when the certificate holds; then
+// pgn = -A^-1 b and *pnorm = |pgn|.
+BLSQ_HD bool tall_gn_try(const Blk& B, const double* A, const TallWork& W, double m,
+                         double* pgn, double* pnorm) {
+    const int n = W.n;
+    double fa = 0.0;
+    bool bad = false;
+    for (int e = B.tid; e < n * n; e += B.nt) {
+        const int i = e / n, j = e % n;
+        if (j >= i) fa = fma(A[e], A[e], fa);
+        if (i == j && !(A[e] != 0.0)) bad = true;
+    }
+    fa = blk_sum(B, fa);
+    if (blk_any(B, bad) || m < n) return false;
+    double ft = 0.0;
+    double* t = W.rowbuf + (size_t)B.warp * n;       // this warp's solution vector
+    for (int c = B.warp; c <= n; c += B.nwarps) {    // c == n: right-hand side b
+        const int top = (c < n) ? c : n - 1;         // e_c has no entries below row c
+        double nn = 0.0;
+        for (int i = top; i >= 0; i--) {
+            const double* ai = A + (size_t)i * n;
+            double acc = 0.0;
+            for (int k = i + 1 + B.lane; k <= top; k += B.lanes) acc = fma(ai[k], t[k], acc);
+            acc = warp_sum(acc);
+            const double rhs = (c < n) ? (i == c ? 1.0 : 0.0) : W.b[i];
+            const double ti = (rhs - acc) / ai[i];
+            if (B.lane == 0) t[i] = ti;
+            nn = fma(ti, ti, nn);
+#if BLSQ_TALL_DEV
+            __syncwarp();
+#endif
+        }
+        if (c < n) {
+            ft += nn;                                 // same value on every lane
+        } else {
+            for (int i = B.lane; i < n; i += B.lanes) pgn[i] = -t[i];
+            if (B.lane == 0) *pnorm = sqrt(nn);
+        }
+    }
+    // ft was accumulated identically by all lanes of a warp: count it once
+    ft = blk_sum(B, B.lane == 0 ? ft : 0.0);
+    B.sync();
+    const double em = EPS * m;
+    return fa * ft * (em * em) < 0.0625;              // false for NaN / inf too
 }
 
 // trust_region.py:47-53 over the block
@@ -746,17 +810,41 @@ BLSQ_HD void tall_trf_propose(const Blk& B, const TallParams& P, const TallWork&
         B.sync();
         return;
     }
+    const double Delta = st[TS_DELTA];
+    double alpha = st[TS_ALPHA];
+    int gn = ist[TI_GN];
+    B.sync();
     if (new_lin) {
-        const int sweeps = tall_hat_svd(B, R, W, A, S, SUF, VT);
-        if (B.tid == 0) ist[TI_SWEEPS] = sweeps;
+        // Gauss-Newton shortcut first (no singular values needed, ~75 % of the
+        // C4 solves); the SVD only when the step is not certified or too long
+        tall_hat_fold(B, R, W, A);
+        gn = tall_gn_try(B, A, W, P.m, SUF, st + TS_GNSTEP) ? 1 : 0;
+        if (!gn) {
+            const int sweeps = tall_hat_finish(B, W, A, S, SUF, VT);
+            if (B.tid == 0) ist[TI_SWEEPS] = sweeps;
+        }
+        B.sync();
+        if (B.tid == 0) ist[TI_GN] = gn;
+    }
+    bool took_gn = false;
+    if (gn) {
+        // the decision is left to the SVD route when |p| is within 1e-9 of
+        // Delta, so that it is always taken with the reference's arithmetic
+        if (st[TS_GNSTEP] <= Delta * (1.0 - 1e-9)) {
+            for (int i = B.tid; i < n; i += B.nt) W.p_h[i] = SUF[i];
+            alpha = 0.0;                              // trust_region.py:117
+            took_gn = true;
+        } else {
+            if (!new_lin) tall_hat_fold(B, R, W, A);  // a rejected trial shrank Delta
+            B.sync();
+            const int sweeps = tall_hat_finish(B, W, A, S, SUF, VT);
+            if (B.tid == 0) { ist[TI_SWEEPS] = sweeps; ist[TI_GN] = 0; }
+        }
     }
     double theta = 1.0 - g_norm;
     if (theta < 0.995) theta = 0.995;
-
-    const double Delta = st[TS_DELTA];
-    double alpha = st[TS_ALPHA];
     B.sync();
-    tall_solve_tr(B, W, P.m, S, SUF, VT, Delta, alpha);
+    if (!took_gn) tall_solve_tr(B, W, P.m, S, SUF, VT, Delta, alpha);
     B.sync();
     for (int i = B.tid; i < n; i += B.nt) W.p[i] = W.d[i] * W.p_h[i];
     B.sync();

@@ -10,7 +10,8 @@ y = torch.randn(m, dtype=torch.float64, device=dev)
 x = torch.rand(n, dtype=torch.float64, device=dev)
 F = torch.empty(m, dtype=torch.float64, device=dev)
 ref = None
-for path in sorted(glob.glob(os.path.join(ROOT, "tools/variants/libmodels_u*.so"))):
+paths = sys.argv[1:] or sorted(glob.glob(os.path.join(ROOT, "tools/variants/libmodels_*.so")))
+for path in paths:
     lib = C.CDLL(path)
     f = lib.blsq_model_linexp_fun
     f.argtypes = [C.c_int64, C.c_int] + [C.c_void_p] * 6
