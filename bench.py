@@ -59,6 +59,11 @@ WORKLOADS = {
     "c4": dict(desc="tall single problem: m=16M rows, n=64, bounded "
                     "linear+exponential model, TRF, row-sharded Cholesky QR on "
                     "FP64 tensor cores", kind="tall", m=1 << 24, n=64, method="trf"),
+    # BASELINE.json configs[4]: 8-GPU configuration (12.5M rows = 51 GB per
+    # GPU); lb = 0 puts half of the U(-1, 1) truth values outside the bounds
+    "c5": dict(desc="tall single problem: m=100M rows, n=256, half the bounds "
+                    "active, row-sharded across the GPUs", kind="tall",
+               m=100_000_000, n=256, method="trf", lb=0.0, no_e2e=True),
 }
 
 
@@ -239,6 +244,16 @@ class ClockSampler:
 TALL_METRIC = "TRF iterations/sec at m=16M, n=64 (tall)"
 
 
+def _ncu_traffic(workload):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu
+    capture (profiles/ncu_traffic.json), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as fh:
+            return json.load(fh).get(workload)
+    except Exception:
+        return None
+
+
 def _peaks():
     try:
         return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -334,7 +349,9 @@ def run_tall(args, w, standalone=True):
     n = w["n"]
     m_total = args.rows or w["m"]
     rows = m_total // world                      # "strong": total rows fixed
-    wl = TallLinExpDevice(rows, n, dev, seed=rank)
+    wl = TallLinExpDevice(rows, n, dev, seed=rank, lb=w.get("lb", -0.5))
+    if args.method:
+        w = dict(w, method=args.method)
     x0 = torch.as_tensor(wl.x0, device=dev)
     lb = torch.as_tensor(wl.lb, device=dev)
     ub = torch.as_tensor(wl.ub, device=dev)
@@ -397,27 +414,29 @@ def run_tall(args, w, standalone=True):
     ach = flops / (gram_ms * 1e-3) / 1e12 if gram_ms else None
 
     # end to end: the problem data comes from pinned host memory every step
-    A_h = wl.A_t.cpu().pin_memory()
-    t_h = wl.t_t.cpu().pin_memory()
-    y_h = wl.y_t.cpu().pin_memory()
-    x_out = torch.empty(n, dtype=torch.float64).pin_memory()
-    barrier()
-    e2 = torch.cuda.Event(enable_timing=True)
-    e3 = torch.cuda.Event(enable_timing=True)
-    e2.record()
-    its_e2e = 0
-    for _ in range(args.steps):
-        wl.load(A_h.to(dev, non_blocking=True), t_h.to(dev, non_blocking=True),
-                y_h.to(dev, non_blocking=True))
-        r = solve()
-        x_out.copy_(r.x, non_blocking=True)
-        torch.cuda.synchronize()
-        its_e2e += r.njev
-    e3.record()
-    barrier()
-    e2e_ms = reduce_max(e2.elapsed_time(e3))
-    h2d = (A_h.numel() + t_h.numel() + y_h.numel()) * 8
-    del A_h, t_h, y_h
+    # (skipped for C5: 8 x 25 GB of pinned host memory)
+    its_e2e, e2e_ms, h2d = 0, None, 0
+    if not w.get("no_e2e"):
+        A_h = wl.A_t.cpu().pin_memory()
+        t_h = wl.t_t.cpu().pin_memory()
+        y_h = wl.y_t.cpu().pin_memory()
+        x_out = torch.empty(n, dtype=torch.float64).pin_memory()
+        barrier()
+        e2 = torch.cuda.Event(enable_timing=True)
+        e3 = torch.cuda.Event(enable_timing=True)
+        e2.record()
+        for _ in range(args.steps):
+            wl.load(A_h.to(dev, non_blocking=True), t_h.to(dev, non_blocking=True),
+                    y_h.to(dev, non_blocking=True))
+            r = solve()
+            x_out.copy_(r.x, non_blocking=True)
+            torch.cuda.synchronize()
+            its_e2e += r.njev
+        e3.record()
+        barrier()
+        e2e_ms = reduce_max(e2.elapsed_time(e3))
+        h2d = (A_h.numel() + t_h.numel() + y_h.numel()) * 8
+        del A_h, t_h, y_h
     if rank != 0:
         if world > 1 and standalone:
             dist.destroy_process_group()
@@ -434,7 +453,9 @@ def run_tall(args, w, standalone=True):
                          f"= {v:.3f} it/s, scaled linearly in m to m={m_total} "
                          f"(extrapolated)"}
     line = {
-        "metric": TALL_METRIC, "value": value, "unit": "iterations/s",
+        "metric": TALL_METRIC if n == 64 else
+        "%s iterations/sec at m=%d, n=%d (tall)" % (w["method"].upper(), m_total, n),
+        "value": value, "unit": "iterations/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64",
@@ -448,15 +469,17 @@ def run_tall(args, w, standalone=True):
                    "nfev_per_step": nfev / args.steps, "status": int(res.status),
                    "l2": "J (%.1f GB per GPU) exceeds the 126 MB L2"
                          % (rows * n * 8 / 1e9)},
-        "e2e": {"value": its_e2e / (e2e_ms * 1e-3), "unit": "iterations/s",
-                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": n * 8,
-                "ms_per_step": e2e_ms / args.steps},
+        "e2e": ({"value": its_e2e / (e2e_ms * 1e-3), "unit": "iterations/s",
+                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": n * 8,
+                 "ms_per_step": e2e_ms / args.steps} if e2e_ms else None),
         "gpu_launches": launches,
         "roofline": {
-            "bound": "tensor", "kernel": "gram_kernel<8,1> + gram_kernel<8,2> "
+            "bound": "tensor", "kernel": "gram_kernel<%d,1> + gram_kernel<%d,2> " % ((n + 7) // 8, (n + 7) // 8) +
                                          "(Cholesky QR of [J | f], FP64 DMMA)",
             "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-            "frac": (ach / peak) if ach else None, "traffic": None,
+            "frac": (ach / peak) if ach else None,
+            "traffic": (_ncu_traffic("c4") or {}).get("bytes_per_launch"),
+            "traffic_source": _ncu_traffic("c4"),
             "peak_source": peak_src,
             "algorithmic_flops_per_jacobian": 2.0 * rows * n * n,
             "route": "preconditioned Cholesky QR: pass 1 on a 1/8 row sample, "
@@ -499,6 +522,8 @@ def main():
                     help="write the per-round CUDA-event timings of the "
                          "instrumented step (running problems, callbacks / "
                          "linearise / round ms) to this CSV file")
+    ap.add_argument("--method", default=None, choices=["trf", "dogbox"],
+                    help="tall workloads: override the method (C5: TRF vs dogbox)")
     ap.add_argument("--rows", type=int, default=None,
                     help="tall workload: total rows (default 2^24)")
     args = ap.parse_args()
@@ -676,7 +701,8 @@ def main():
         "bound": "hbm", "kernel": "lin_kernel (blsq_linearise_batched)",
         "achieved": lin.get("gbs"), "peak": peak, "unit": "GB/s",
         "frac": (lin.get("gbs") / peak) if lin.get("gbs") else None,
-        "traffic": None, "peak_source": peak_src,
+        "traffic": (_ncu_traffic(args.workload) or {}).get("bytes_per_launch"),
+        "traffic_source": _ncu_traffic(args.workload), "peak_source": peak_src,
         "algorithmic_bytes_per_problem": lin.get("bytes_per_problem"),
         "avg_launch_ms": lin.get("avg_ms"), "launches": lin.get("launches"),
         "share_of_kernel_time": lin.get("share"),
