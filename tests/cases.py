@@ -650,3 +650,44 @@ def check_benchmark_table(lib, dev, out_path):
     text = open(out_path).read()
     assert "Bounded problems" in text and "g norm" in text
     return dict(checked=checked, unsupported=unsupported)
+
+
+# --------------------------------------------- device-side compaction ABI --
+
+def check_compact_batched(lib, dev, seed=9):
+    """blsq_compact_batched against NumPy: survivors keep their order, ids and
+    trial points move together; with and without an input index list and Xjac,
+    sizes around the block boundaries of the kernel."""
+    rng = np.random.default_rng(seed)
+    for A, n, with_idx, with_j in ((1, 3, False, False), (1023, 4, False, True),
+                                   (1024, 4, True, False), (1025, 6, True, True),
+                                   (40000, 2, True, True), (5000, 8, False, False)):
+        Btot = A * 2 if with_idx else A
+        status = np.where(rng.random(Btot) < 0.6, -1, 2).astype(np.int32)
+        istate = np.zeros((Btot, 8), np.int32)
+        istate[:, 0] = status
+        idx = np.sort(rng.choice(Btot, A, replace=False)).astype(np.int32) if with_idx else None
+        X = rng.standard_normal((A, n))
+        Xj = rng.standard_normal((A, n)) if with_j else None
+        ti = torch.as_tensor(istate, device=dev)
+        tx, tj = T(X, dev), (T(Xj, dev) if with_j else None)
+        tidx = torch.as_tensor(idx, device=dev) if with_idx else None
+        o32 = torch.full((A,), -7, dtype=torch.int32, device=dev)
+        o64 = torch.full((A,), -7, dtype=torch.int64, device=dev)
+        ox = torch.zeros((A, n), dtype=torch.float64, device=dev)
+        oj = torch.zeros((A, n), dtype=torch.float64, device=dev) if with_j else None
+        work = torch.empty(int(lib._dll.blsq_compact_work_size(A)), dtype=torch.int32,
+                           device=dev)
+        lib.call("blsq_compact_batched", A, None if tidx is None else tidx.data_ptr(),
+                 ti.data_ptr(), n, tx.data_ptr(), None if tj is None else tj.data_ptr(),
+                 o32.data_ptr(), o64.data_ptr(), ox.data_ptr(),
+                 None if oj is None else oj.data_ptr(), work.data_ptr(), lib.stream(tx))
+        pid = idx.astype(np.int64) if with_idx else np.arange(A)
+        keep = status[pid] == -1
+        k = int(keep.sum())
+        assert np.array_equal(o32.cpu().numpy()[:k], pid[keep].astype(np.int32)), (A, n)
+        assert np.array_equal(o64.cpu().numpy()[:k], pid[keep]), (A, n)
+        assert bits(ox.cpu().numpy()[:k], X[keep]), (A, n)
+        if with_j:
+            assert bits(oj.cpu().numpy()[:k], Xj[keep]), (A, n)
+        assert (o32.cpu().numpy()[k:] == -7).all()

@@ -71,3 +71,7 @@ def test_benchmark_table(lib, tmp_path):
     st = cases.check_benchmark_table(lib, DEV, tmp_path / "table.txt")
     print(st)
     assert st["checked"] >= 30
+
+
+def test_compact_batched(lib):
+    cases.check_compact_batched(lib, DEV)

@@ -207,3 +207,7 @@ def test_benchmark_table(lib, dev, tmp_path):
     st = cases.check_benchmark_table(lib, dev, tmp_path / "table.txt")
     print(st)
     assert st["checked"] >= 30
+
+
+def test_compact_batched(lib, dev):
+    cases.check_compact_batched(lib, dev)
