@@ -13,10 +13,11 @@ expdecay2_kernel(int64_t A, const int64_t* __restrict__ idx, int m,
                  const double* __restrict__ t, const double* __restrict__ X,
                  const double* __restrict__ y, double* __restrict__ F,
                  double* __restrict__ J) {
-    int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= A * m) return;
-    int64_t s = g / m;
-    int r = (int)(g % m);
+    // block = (rows, problems): no 64-bit division per element
+    const int64_t s = (int64_t)blockIdx.x * blockDim.y + threadIdx.y;
+    const int r = blockIdx.y * blockDim.x + threadIdx.x;
+    if (s >= A || r >= m) return;
+    const int64_t g = s * m + r;
     int64_t pid = idx ? idx[s] : s;
     const double4 x = *reinterpret_cast<const double4*>(X + s * 4);
     const double tr = t[r];
@@ -35,10 +36,10 @@ __global__ void __launch_bounds__(256)
 gausspeak_kernel(int64_t A, const int64_t* __restrict__ idx, int m,
                  const double* __restrict__ t, const double* __restrict__ X,
                  const double* __restrict__ y, double* __restrict__ F) {
-    int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= A * m) return;
-    int64_t s = g / m;
-    int r = (int)(g % m);
+    const int64_t s = (int64_t)blockIdx.x * blockDim.y + threadIdx.y;
+    const int r = blockIdx.y * blockDim.x + threadIdx.x;
+    if (s >= A || r >= m) return;
+    const int64_t g = s * m + r;
     int64_t pid = idx ? idx[s] : s;
     const double* x = X + s * 6;
     const double tr = t[r];
@@ -171,6 +172,20 @@ linexp_jac_kernel(int64_t m, int n, double* __restrict__ J, const double* __rest
     }
 }
 
+// 256 threads as (rows of a problem, problems): x covers min(m, 256) rows
+// rounded up to a warp, y the problems that fit beside it
+bool batched_model_grid(int64_t A, int m, dim3& block, dim3& grid) {
+    int bx = m < 256 ? ((m + 31) / 32) * 32 : 256;
+    int by = 256 / bx;
+    if (by < 1) by = 1;
+    const int64_t gx = (A + by - 1) / by;
+    const int64_t gy = (m + bx - 1) / bx;
+    if (gx > 0x7fffffff || gy > 65535) return false;
+    block = dim3(bx, by, 1);
+    grid = dim3((unsigned)gx, (unsigned)gy, 1);
+    return true;
+}
+
 }  // namespace
 
 extern "C" {
@@ -180,10 +195,9 @@ int blsq_model_expdecay2(int64_t A, const int64_t* idx, int m, const double* t,
                          void* stream) {
     if (A < 0 || m < 1 || !t || !X || !y || !F) return BLSQ_E_BADARG;
     if (A == 0) return 0;
-    int64_t blocks = (A * m + 255) / 256;
-    if (blocks > 0x7fffffff) return BLSQ_E_UNSUPPORTED;
-    expdecay2_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
-        A, idx, m, t, X, y, F, J);
+    dim3 block, grid;
+    if (!batched_model_grid(A, m, block, grid)) return BLSQ_E_UNSUPPORTED;
+    expdecay2_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(A, idx, m, t, X, y, F, J);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : (int)e;
 }
@@ -193,10 +207,9 @@ int blsq_model_gausspeak(int64_t A, const int64_t* idx, int m, const double* t,
                          void* stream) {
     if (A < 0 || m < 1 || !t || !X || !y || !F) return BLSQ_E_BADARG;
     if (A == 0) return 0;
-    int64_t blocks = (A * m + 255) / 256;
-    if (blocks > 0x7fffffff) return BLSQ_E_UNSUPPORTED;
-    gausspeak_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
-        A, idx, m, t, X, y, F);
+    dim3 block, grid;
+    if (!batched_model_grid(A, m, block, grid)) return BLSQ_E_UNSUPPORTED;
+    gausspeak_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(A, idx, m, t, X, y, F);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : (int)e;
 }
