@@ -296,23 +296,18 @@ lin_kernel(int64_t A, const int32_t* __restrict__ idx, int m,
 // that need the SVD route to work[1..] (work[0] = their number); MODE 2 then
 // finishes exactly those slots with dense warps (blsq_core.cuh trf_round_impl).
 template <int N, int METHOD, int MODE>
-__global__ void __launch_bounds__(BLSQ_ROUND_THREADS, BLSQ_ROUND_MINB)
-round_kernel(int64_t A, const int32_t* __restrict__ idx,
-             const double* __restrict__ lin, const double* __restrict__ x0,
-             const double* __restrict__ lb, const double* __restrict__ ub,
-             int bstride, const double* __restrict__ scaling, SolveParams P,
-             int first, double* __restrict__ state,
-             int32_t* __restrict__ istate, double* __restrict__ Xnew,
-             double* __restrict__ Xjac, int32_t* __restrict__ work) {
+__device__ __forceinline__ void
+round_slot(int64_t slot, int64_t A, const int32_t* __restrict__ idx,
+           const double* __restrict__ lin, const double* __restrict__ x0,
+           const double* __restrict__ lb, const double* __restrict__ ub,
+           int bstride, const double* __restrict__ scaling, const SolveParams& P,
+           int first, double* __restrict__ state,
+           int32_t* __restrict__ istate, double* __restrict__ Xnew,
+           double* __restrict__ Xjac, int32_t* __restrict__ work) {
     typedef LinRec<N> L;
     constexpr int SS = (METHOD == BLSQ_METHOD_TRF) ? TrfState<N>::SIZE
                                                    : DogState<N>::SIZE;
     constexpr int XNEW = N;
-    int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (MODE == 2) {
-        if (slot >= work[0]) return;
-        slot = work[1 + slot];
-    }
     if (slot >= A) return;
     const int64_t pid = idx ? idx[slot] : slot;
     int ist[IS_SIZE];
@@ -388,6 +383,29 @@ round_kernel(int64_t A, const int32_t* __restrict__ idx,
                 Xjac[slot * N + i] = xj;
             }
         }
+    }
+}
+
+template <int N, int METHOD, int MODE>
+__global__ void __launch_bounds__(BLSQ_ROUND_THREADS, BLSQ_ROUND_MINB)
+round_kernel(int64_t A, const int32_t* __restrict__ idx,
+             const double* __restrict__ lin, const double* __restrict__ x0,
+             const double* __restrict__ lb, const double* __restrict__ ub,
+             int bstride, const double* __restrict__ scaling, SolveParams P,
+             int first, double* __restrict__ state,
+             int32_t* __restrict__ istate, double* __restrict__ Xnew,
+             double* __restrict__ Xjac, int32_t* __restrict__ work) {
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (MODE == 2) {
+        // the worklist length is only known on the device: a small grid
+        // strides over it
+        const int64_t cnt = work[0];
+        for (int64_t w = tid; w < cnt; w += (int64_t)gridDim.x * blockDim.x)
+            round_slot<N, METHOD, MODE>(work[1 + w], A, idx, lin, x0, lb, ub, bstride, scaling,
+                                        P, first, state, istate, Xnew, Xjac, work);
+    } else {
+        round_slot<N, METHOD, MODE>(tid, A, idx, lin, x0, lb, ub, bstride, scaling, P, first,
+                                    state, istate, Xnew, Xjac, work);
     }
 }
 
@@ -598,9 +616,10 @@ int launch_round(int method, int64_t A, const int32_t* idx, const double* lin,
         round_kernel<N, BLSQ_METHOD_TRF, 1><<<gb, BLSQ_ROUND_THREADS, 0, s>>>(
             A, idx, lin, x0, lb, ub, bstride, scaling, P, first, state, istate, Xnew, Xjac, work);
         BLSQ_LAUNCH_CHECK();
-        // the worklist length is only known on the device: full grid, the
-        // blocks past work[0] exit at once
-        round_kernel<N, BLSQ_METHOD_TRF, 2><<<gb, BLSQ_ROUND_THREADS, 0, s>>>(
+        // ~5 % of the problems land on the worklist: an eighth of the grid
+        // (at least 4 CTAs per SM) strides over it
+        unsigned g2 = gb / 8 > 592u ? gb / 8 : (gb < 592u ? gb : 592u);
+        round_kernel<N, BLSQ_METHOD_TRF, 2><<<g2, BLSQ_ROUND_THREADS, 0, s>>>(
             A, idx, lin, x0, lb, ub, bstride, scaling, P, first, state, istate, Xnew, Xjac, work);
     } else if (method == BLSQ_METHOD_TRF) {
         round_kernel<N, BLSQ_METHOD_TRF, 0><<<gb, BLSQ_ROUND_THREADS, 0, s>>>(

@@ -1101,29 +1101,35 @@ BLSQ_HD bool dogbox_round(double* st, int* ist, const double* lin,
             A[i * N + j] = (j >= i && free_[j])
                                ? st[S::R + tri_index<N>(i, j)] : 0.0;
     }
-    jacobi_rows<N>(A, bq);          // rows: s_j v_j^T ; bq: U^T (Q^T f)
-    double sv2[N], smax2 = 0.0;
-    BLSQ_UNROLL
-    for (int j = 0; j < N; j++) {
-        double nn = 0.0;
-        BLSQ_UNROLL
-        for (int i = 0; i < N; i++) nn = fma(A[j * N + i], A[j * N + i], nn);
-        sv2[j] = nn;                 // s_j^2
-        if (nn > smax2) smax2 = nn;
-    }
-    int mx = P.m > nfree ? P.m : nfree;
-    double cut = EPS * mx * sqrt(smax2);
-    double w[N];
-    BLSQ_UNROLL
-    for (int j = 0; j < N; j++)
-        w[j] = (sqrt(sv2[j]) > cut) ? bq[j] / sv2[j] : 0.0;
     double newton[N], cauchy[N];
-    BLSQ_UNROLL
-    for (int i = 0; i < N; i++) {
-        double acc = 0.0;
+    // No variable on a bound and full rank certified (cond(R) <= |R|_F |R^-1|_F
+    // with a factor 4 to spare against numpy's rcond = eps * max(m, n)): the
+    // minimum-norm solution is the least-squares solution -R^-1 Q^T f and no
+    // singular value is dropped -- no SVD needed (see gn_shortcut).
+    if (!(nfree == N && gn_shortcut<N>(A, bq, P.m, dinf(), newton))) {
+        jacobi_rows<N>(A, bq);          // rows: s_j v_j^T ; bq: U^T (Q^T f)
+        double sv2[N], smax2 = 0.0;
         BLSQ_UNROLL
-        for (int j = 0; j < N; j++) acc = fma(A[j * N + i], w[j], acc);
-        newton[i] = free_[i] ? -acc : 0.0;
+        for (int j = 0; j < N; j++) {
+            double nn = 0.0;
+            BLSQ_UNROLL
+            for (int i = 0; i < N; i++) nn = fma(A[j * N + i], A[j * N + i], nn);
+            sv2[j] = nn;                 // s_j^2
+            if (nn > smax2) smax2 = nn;
+        }
+        int mx = P.m > nfree ? P.m : nfree;
+        double cut = EPS * mx * sqrt(smax2);
+        double w[N];
+        BLSQ_UNROLL
+        for (int j = 0; j < N; j++)
+            w[j] = (sqrt(sv2[j]) > cut) ? bq[j] / sv2[j] : 0.0;
+        BLSQ_UNROLL
+        for (int i = 0; i < N; i++) {
+            double acc = 0.0;
+            BLSQ_UNROLL
+            for (int j = 0; j < N; j++) acc = fma(A[j * N + i], w[j], acc);
+            newton[i] = free_[i] ? -acc : 0.0;
+        }
     }
     // cauchy = -(g.g)/(Jg.Jg) g  (dogbox.py:198-199), |J_free g| = |R g_free|
     double gf[N], Jg[N];
