@@ -589,7 +589,8 @@ def main():
             yc = y_any[c0:c0 + chunk]
             opts = dict(timers=collect) if collect is not None else {}
             if not x0_any.is_cuda:
-                opts.update(h2d_chunks=4, device=dev,
+                opts.update(h2d_chunks=int(os.environ.get("BLSQ_BENCH_H2D_CHUNKS", "4")),
+                            device=dev,
                             prologue_rounds=w.get("prologue_rounds", 6))
             res = least_squares_batched(
                 fun, x0_any[c0:c0 + chunk], jac=jac, bounds=(lb, ub),
