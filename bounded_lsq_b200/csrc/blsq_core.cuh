@@ -443,17 +443,25 @@ BLSQ_HD bool gn_shortcut(const double* A, const double* b, int m, double Delta,
     }
     const double em = EPS * m;
     if (!(fa * ft * (em * em) < 0.0625)) return false;     // also rejects NaN / inf
+    // p = -A^-1 b by back substitution; the quotient by a_ii is the correctly
+    // rounded one (reciprocal + one FMA correction, Markstein), so that for
+    // n = 1 the step is bit for bit the reference's -V (uf / s) = -b / a
+    // (its own test_diff_step compares two solves with assert_equal)
     double nn = 0.0;
     BLSQ_UNROLL
-    for (int i = 0; i < N; i++) {
-        double acc = 0.0;
+    for (int ii = 0; ii < N; ii++) {
+        const int i = N - 1 - ii;
+        double num = -b[i];
         BLSQ_UNROLL
         for (int j = 0; j < N; j++) {
-            if (j < i) continue;
-            acc = fma(T[i * N + j], b[j], acc);
+            if (j <= i) continue;
+            num = fma(-A[i * N + j], p_h[j], num);
         }
-        p_h[i] = -acc;
-        nn = fma(acc, acc, nn);
+        const double r = T[i * N + i];
+        double q = num * r;
+        q = fma(fma(-q, A[i * N + i], num), r, q);
+        p_h[i] = q;
+        nn = fma(q, q, nn);
     }
     return sqrt(nn) <= Delta * (1.0 - 1e-9);
 }
