@@ -7,6 +7,7 @@ branch logic is exercised in the GPU-less container.
 """
 import json
 import os
+import warnings
 
 import numpy as np
 import torch
@@ -251,9 +252,18 @@ def check_graph_tail_invariance(lib, dev):
             return model.fun_t(X, yy)
 
         base = solve(graph_tail_rounds=0)
-        for label, r in (("graph8", solve()),
-                         ("graph3", solve(graph_tail_rounds=3, tail_below=2000)),
-                         ("fallback", solve(fun=syncing_fun))):
+        with warnings.catch_warnings(record=True) as caught:
+            warnings.simplefilter("always")
+            r_fallback = solve(fun=syncing_fun)
+        assert any("could not be captured" in str(w.message) for w in caught)
+        # ... and a failed capture must not poison the next one
+        with warnings.catch_warnings(record=True) as caught:
+            warnings.simplefilter("always")
+            r_g8 = solve()
+            r_g3 = solve(graph_tail_rounds=3, tail_below=2000)
+        assert not any("could not be captured" in str(w.message) for w in caught), \
+            [str(w.message) for w in caught]
+        for label, r in (("graph8", r_g8), ("graph3", r_g3), ("fallback", r_fallback)):
             for fld in ("x", "obj_value", "status", "nfev", "njev", "active_mask"):
                 assert bits(getattr(r, fld).cpu().numpy(),
                             getattr(base, fld).cpu().numpy()), (cfg, label, fld)
@@ -632,7 +642,7 @@ def check_benchmark_table(lib, dev, out_path):
         "blsq_run_benchmarks", os.path.join(root, "benchmarks", "run_benchmarks.py"))
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
-    rows = mod.main([str(out_path), "-b"], lib=lib, dev=dev)
+    rows = mod.main([str(out_path)], lib=lib, dev=dev)      # unbounded + bounded
     z = np.load(os.path.join(GOLDEN, "corpus.npz"))
     checked = unsupported = 0
     for name, meth, r in rows:
@@ -641,14 +651,19 @@ def check_benchmark_table(lib, dev, out_path):
             continue
         if name in CHAOTIC or name.split("_")[0] in CHAOTIC:
             continue
-        obj, status, nfev, njev, opt, ntr = z[f"{name}|{meth}|exact|1|scalars"]
-        mask = z[f"{name}|{meth}|exact|1|mask"]
+        solver, sc = (meth[:-2], "jac") if meth.endswith("-s") else (meth, "1")
+        key = f"{name}|{solver}|exact|{sc}|"
+        if key + "scalars" not in z.files:
+            continue
+        obj, status, nfev, njev, opt, ntr = z[key + "scalars"]
+        mask = z[key + "mask"]
         assert r[4] == int(status) and r[0] == int(nfev), (name, meth, r)
         assert abs(r[2] - obj) <= 1e-8 * obj + 1e-18, (name, meth, r, obj)
         assert r[3] == int(np.count_nonzero(mask)), (name, meth, r)
         checked += 1
     text = open(out_path).read()
-    assert "Bounded problems" in text and "g norm" in text
+    assert "Bounded problems" in text and "Unbounded problems" in text
+    assert "g norm" in text
     return dict(checked=checked, unsupported=unsupported)
 
 

@@ -70,7 +70,7 @@ def test_tall_options_vs_oracle(lib):
 def test_benchmark_table(lib, tmp_path):
     st = cases.check_benchmark_table(lib, DEV, tmp_path / "table.txt")
     print(st)
-    assert st["checked"] >= 30
+    assert st["checked"] >= 60
 
 
 def test_compact_batched(lib):

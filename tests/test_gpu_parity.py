@@ -206,7 +206,7 @@ def test_tall_options_vs_oracle(lib, dev):
 def test_benchmark_table(lib, dev, tmp_path):
     st = cases.check_benchmark_table(lib, dev, tmp_path / "table.txt")
     print(st)
-    assert st["checked"] >= 30
+    assert st["checked"] >= 60
 
 
 def test_compact_batched(lib, dev):
