@@ -503,48 +503,130 @@ BLSQ_HD int tall_hat_svd(const Blk& B, const double* R, const TallWork& W, doubl
 // side, b; row i of a solve is a lane-parallel dot product over the part of the
 // solution that exists already.  Returns true when the certificate holds; then
 // pgn = -A^-1 b and *pnorm = |pgn|.
-BLSQ_HD bool tall_gn_try(const Blk& B, const double* A, const TallWork& W, double m,
-                         double* pgn, double* pnorm) {
+// A is n x n row major; the triangle that is solved is T[i][k] = A[i][cm[k]]
+// (cm == nullptr: identity) for 0 <= i <= k < nn, the right-hand side W.b[0..nn).
+BLSQ_HD bool tall_tri_try(const Blk& B, const double* A, const TallWork& W, int nn,
+                          const int* cm, double em, double* pgn, double* pnorm) {
     const int n = W.n;
     double fa = 0.0;
     bool bad = false;
-    for (int e = B.tid; e < n * n; e += B.nt) {
-        const int i = e / n, j = e % n;
-        if (j >= i) fa = fma(A[e], A[e], fa);
-        if (i == j && !(A[e] != 0.0)) bad = true;
+    for (int e = B.tid; e < nn * nn; e += B.nt) {
+        const int i = e / nn, k = e % nn;
+        if (k < i) continue;
+        const double a = A[(size_t)i * n + (cm ? cm[k] : k)];
+        fa = fma(a, a, fa);
+        if (i == k && !(a != 0.0)) bad = true;
     }
     fa = blk_sum(B, fa);
-    if (blk_any(B, bad) || m < n) return false;
+    if (blk_any(B, bad)) return false;
     double ft = 0.0;
     double* t = W.rowbuf + (size_t)B.warp * n;       // this warp's solution vector
-    for (int c = B.warp; c <= n; c += B.nwarps) {    // c == n: right-hand side b
-        const int top = (c < n) ? c : n - 1;         // e_c has no entries below row c
-        double nn = 0.0;
+    for (int c = B.warp; c <= nn; c += B.nwarps) {   // c == nn: right-hand side b
+        const int top = (c < nn) ? c : nn - 1;       // e_c has no entries below row c
+        double nrm = 0.0;
         for (int i = top; i >= 0; i--) {
             const double* ai = A + (size_t)i * n;
             double acc = 0.0;
-            for (int k = i + 1 + B.lane; k <= top; k += B.lanes) acc = fma(ai[k], t[k], acc);
+            for (int k = i + 1 + B.lane; k <= top; k += B.lanes)
+                acc = fma(ai[cm ? cm[k] : k], t[k], acc);
             acc = warp_sum(acc);
-            const double rhs = (c < n) ? (i == c ? 1.0 : 0.0) : W.b[i];
-            const double ti = (rhs - acc) / ai[i];
+            const double rhs = (c < nn) ? (i == c ? 1.0 : 0.0) : W.b[i];
+            const double ti = (rhs - acc) / ai[cm ? cm[i] : i];
             if (B.lane == 0) t[i] = ti;
-            nn = fma(ti, ti, nn);
+            nrm = fma(ti, ti, nrm);
 #if BLSQ_TALL_DEV
             __syncwarp();
 #endif
         }
-        if (c < n) {
-            ft += nn;                                 // same value on every lane
+        if (c < nn) {
+            ft += nrm;                                // same value on every lane
         } else {
-            for (int i = B.lane; i < n; i += B.lanes) pgn[i] = -t[i];
-            if (B.lane == 0) *pnorm = sqrt(nn);
+            for (int i = B.lane; i < nn; i += B.lanes) pgn[i] = -t[i];
+            if (B.lane == 0) *pnorm = sqrt(nrm);
         }
     }
     // ft was accumulated identically by all lanes of a warp: count it once
     ft = blk_sum(B, B.lane == 0 ? ft : 0.0);
     B.sync();
-    const double em = EPS * m;
     return fa * ft * (em * em) < 0.0625;              // false for NaN / inf too
+}
+
+BLSQ_HD bool tall_gn_try(const Blk& B, const double* A, const TallWork& W, double m,
+                         double* pgn, double* pnorm) {
+    if (m < W.n) return false;
+    return tall_tri_try(B, A, W, W.n, nullptr, EPS * m, pgn, pnorm);
+}
+
+// dogbox.py:197, newton_step = lstsq(J_free, -f)[0], without singular values:
+// Householder QR of the free columns of R (a staircase: column fl[c] has
+// entries down to row fl[c] only), the same reflectors on Q^T f, then the
+// certified triangular solve of tall_tri_try against numpy's
+// rcond = eps * max(m, n_free).  One thread per trailing column (coalesced
+// along the rows of A), ~3 block barriers per column.  Returns false when the
+// certificate fails (the caller then takes the SVD route, which rebuilds A).
+BLSQ_HD bool tall_dogbox_ls(const Blk& B, const double* R, const TallWork& W, double* A,
+                            int nfree, double m, double* newton, double* pnorm_slot) {
+    const int n = W.n;
+    int* fl = W.hits;                                 // free columns, ascending
+    for (int e = B.tid; e < n * n; e += B.nt) {
+        const int i = e / n, j = e % n;
+        A[e] = (j >= i && W.fr[j]) ? R[e] : 0.0;
+    }
+    for (int i = B.tid; i < n; i += B.nt) W.b[i] = W.qtf[i];
+    if (B.tid == 0) {
+        int c = 0;
+        for (int j = 0; j < n; j++)
+            if (W.fr[j]) fl[c++] = j;
+    }
+    B.sync();
+    double* v = W.w;
+    for (int c = 0; c < nfree; c++) {
+        const int jc = fl[c];
+        const int len = jc - c + 1;                   // rows c .. jc
+        if (len <= 1) continue;                       // already triangular here
+        double nn = 0.0;
+        for (int r = B.tid; r < len; r += B.nt) {
+            const double a = A[(size_t)(c + r) * n + jc];
+            v[r] = a;
+            nn = fma(a, a, nn);
+        }
+        nn = blk_sum(B, nn);
+        const double v0 = v[0];
+        const double below = nn - v0 * v0;
+        if (!(below > 0.0)) continue;                 // nothing under the diagonal
+        const double alpha = (v0 > 0.0) ? -sqrt(nn) : sqrt(nn);
+        const double u0 = v0 - alpha;                 // v <- v - alpha e_0
+        const double vtv = below + u0 * u0;
+        const double beta = 2.0 / vtv;
+        B.sync();
+        if (B.tid == 0) v[0] = u0;
+        B.sync();
+        // trailing free columns and the right-hand side (index nfree)
+        for (int cc = c + 1 + B.tid; cc <= nfree; cc += B.nt) {
+            double w = 0.0;
+            if (cc < nfree) {
+                const int j = fl[cc];
+                for (int r = 0; r < len; r++) w = fma(v[r], A[(size_t)(c + r) * n + j], w);
+                w *= beta;
+                for (int r = 0; r < len; r++)
+                    A[(size_t)(c + r) * n + j] = fma(-w, v[r], A[(size_t)(c + r) * n + j]);
+            } else {
+                for (int r = 0; r < len; r++) w = fma(v[r], W.b[c + r], w);
+                w *= beta;
+                for (int r = 0; r < len; r++) W.b[c + r] = fma(-w, v[r], W.b[c + r]);
+            }
+        }
+        if (B.tid == 0) A[(size_t)c * n + jc] = alpha;
+        B.sync();
+    }
+    const double mx = m > nfree ? m : (double)nfree;
+    double* sol = W.suf;
+    if (!tall_tri_try(B, A, W, nfree, fl, EPS * mx, sol, pnorm_slot)) return false;
+    for (int i = B.tid; i < n; i += B.nt) newton[i] = 0.0;
+    B.sync();
+    for (int c = B.tid; c < nfree; c += B.nt) newton[fl[c]] = sol[c];
+    B.sync();
+    return true;
 }
 
 // trust_region.py:47-53 over the block
@@ -1042,6 +1124,7 @@ BLSQ_HD void tall_dogbox_propose(const Blk& B, const TallParams& P, const TallWo
     if (new_lin) {
         // newton_step = lstsq(J_free, -f) (dogbox.py:197): minimum norm through
         // the SVD of R[:, free], numpy rcond = eps * max(m, n_free)
+        if (!(P.m >= nfree && tall_dogbox_ls(B, R, W, A, nfree, P.m, newton, st + TS_GNSTEP))) {
         for (int e = B.tid; e < n * n; e += B.nt) {
             const int i = e / n, j = e % n;
             A[e] = (j >= i && W.fr[j]) ? R[e] : 0.0;
@@ -1067,6 +1150,8 @@ BLSQ_HD void tall_dogbox_propose(const Blk& B, const TallParams& P, const TallWo
         cols_dot(B, A, n, W.w, newton, -1.0);
         B.sync();
         for (int i = B.tid; i < n; i += B.nt) if (!W.fr[i]) newton[i] = 0.0;
+        }
+        B.sync();
         // cauchy = -(g.g)/(Jg.Jg) g (dogbox.py:198-199), |J_free g| = |R g_free| (Q-D5 unguarded)
         tall_Rh_matvec(B, R, n, nullptr, gf, W.t1, Jg);
         double gg = 0.0, jj = 0.0, z = 0.0;
