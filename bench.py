@@ -81,6 +81,7 @@ def _cpu_worker(job):
     _, y = model.make_data(count, seed=seed)
     t0 = time.perf_counter()
     nfev = 0
+    res = []
     for b in range(count):
         if jac == "exact":
             r = orc.least_squares(model.fun_np, model.x0, jac=model.jac_np,
@@ -91,7 +92,8 @@ def _cpu_worker(job):
                                   bounds=(model.lb, model.ub), method=method,
                                   args=(y[b],))
         nfev += r.nfev
-    return count, nfev, time.perf_counter() - t0
+        res.append((r.x, r.status, r.nfev, r.obj_value))
+    return count, nfev, time.perf_counter() - t0, res
 
 
 def cpu_fits_per_second(w, per_core, cores=None, seed0=1000):
@@ -108,7 +110,42 @@ def cpu_fits_per_second(w, per_core, cores=None, seed0=1000):
         out = pool.map(_cpu_worker, jobs)
     wall = time.perf_counter() - t0
     fits = sum(o[0] for o in out)
+    cpu_fits_per_second.last = dict(
+        seeds=[j[3] for j in jobs], per_core=per_core,
+        results=[r for o in out for r in o[3]])
     return fits / wall, cores, fits, sum(o[1] for o in out) / fits
+
+
+def gpu_parity_of_cpu_sample(w, fun, jac, lb, ub, dev):
+    """SURVEY 8(d) "parity gates run with every measurement": the fits the
+    cpu_baseline leg just solved with the oracle, solved again on the GPU."""
+    import torch
+    from bounded_lsq_b200 import least_squares_batched, PerProblem
+    last = getattr(cpu_fits_per_second, "last", None)
+    if not last:
+        return None
+    model = _model(w["model"])
+    y = np.concatenate([model.make_data(last["per_core"], seed=sd)[1]
+                        for sd in last["seeds"]])
+    B = y.shape[0]
+    res = least_squares_batched(
+        fun, torch.as_tensor(np.tile(model.x0, (B, 1)), device=dev), jac=jac,
+        bounds=(lb, ub), method=w["method"],
+        args=(PerProblem(torch.as_tensor(y, device=dev)),))
+    xr = np.array([r[0] for r in last["results"]])
+    st = np.array([r[1] for r in last["results"]])
+    nf = np.array([r[2] for r in last["results"]])
+    ob = np.array([r[3] for r in last["results"]])
+    x = res.x.cpu().numpy()
+    return {
+        "fits": int(B),
+        "status_equal": float((res.status.cpu().numpy() == st).mean()),
+        "nfev_equal": float((res.nfev.cpu().numpy() == nf).mean()),
+        "x_rel_max": float((np.abs(x - xr).max(1) / np.abs(xr).max(1)).max()),
+        "obj_rel_max": float((np.abs(res.obj_value.cpu().numpy() - ob) / ob).max()),
+        "note": "GPU path vs the oracle on the cpu_baseline sample; the gates "
+                "(1e-8 on x / cost, equal status) are enforced in tests/",
+    }
 
 
 def run_reference_arm(args, w):
@@ -727,6 +764,10 @@ def main():
         cpu = {"value": v, "unit": "fits/s", "cores": cores, "kind": "port",
                "sample": f"{fits} fits ({per_core}/core), oracle/blsq_oracle.py"
                          f" NumPy/SciPy restatement, mean nfev {nf:.1f}"}
+        try:
+            cpu["parity_vs_gpu"] = gpu_parity_of_cpu_sample(w, fun, jac, lb, ub, dev)
+        except Exception as e:                    # reporting only
+            cpu["parity_vs_gpu"] = {"error": repr(e)}
 
     line = {
         "metric": "bounded fits solved/sec (batched)", "value": value,
