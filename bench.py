@@ -20,7 +20,8 @@ the two CUDA kernels per round behind include/blsq.h).
   roofline  the HBM-bound linearisation kernel (QR of [J | f] per problem):
          algorithmic bytes / CUDA-event time vs MEASURED_PEAKS.json
   cpu_baseline  the oracle (NumPy port of the reference) on the host cores,
-         bounded sample of the same workload
+         bounded sample of the same workload; parity_vs_gpu = the same fits
+         solved on the GPU and compared with the oracle's results
 
 With N > 1 (torchrun) the problems are split by index, no collective on the
 data path ("weak": per-GPU batch fixed).
