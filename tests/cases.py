@@ -706,3 +706,93 @@ def check_compact_batched(lib, dev, seed=9):
         if with_j:
             assert bits(oj.cpu().numpy()[:k], Xj[keep]), (A, n)
         assert (o32.cpu().numpy()[k:] == -7).all()
+
+
+# ------------------------------------- random small problems vs the oracle --
+
+def check_random_small_vs_oracle(lib, dev, B=20, seed=42):
+    """Random bounded nonlinear problems for every n = 1..8, both methods,
+    fixed and 'jac' scaling, with bounds that are active at many solutions:
+    the batched path against the oracle.  Gates: every solution feasible and
+    its cost within the north-star 1e-8; status, nfev, x (1e-8) and the active
+    set identical for >= 99 % (the rest are evaluations where two termination
+    tests are met within an ulp of each other, SURVEY 7 hard part 1)."""
+    from oracle import blsq_oracle as orc
+    rng = np.random.default_rng(seed)
+    total = exact = 0
+    for n in range(1, 9):
+        for method in ("trf", "dogbox"):
+            for scaling in (1.0, "jac"):
+                m = int(rng.integers(n, 3 * n + 6))
+                A = rng.standard_normal((m, n))
+                Bm = rng.standard_normal((m, n)) * 0.5
+                xt = rng.uniform(-1, 1, (B, n))
+
+                def model(x):
+                    return A @ x + 0.3 * np.sin(Bm @ x)
+                y = np.array([model(xt[b]) for b in range(B)]) + \
+                    0.01 * rng.standard_normal((B, m))
+                lb, ub, x0 = np.full(n, -0.6), np.full(n, 0.7), np.zeros(n)
+                At, Bt = T(A, dev), T(Bm, dev)
+
+                def fun_t(X, Y):
+                    return X @ At.T + 0.3 * torch.sin(X @ Bt.T) - Y
+
+                def jac_t(X, Y):
+                    return At[None] + 0.3 * torch.cos(X @ Bt.T)[:, :, None] * Bt[None]
+                res = least_squares_batched(
+                    fun_t, T(np.tile(x0, (B, 1)), dev), jac=jac_t,
+                    bounds=(T(lb, dev), T(ub, dev)), method=method, scaling=scaling,
+                    args=(PerProblem(T(y, dev)),), _lib=lib)
+                X = res.x.cpu().numpy()
+                assert np.all(X >= lb) and np.all(X <= ub)
+                st, nf = res.status.cpu().numpy(), res.nfev.cpu().numpy()
+                ob, mk = res.obj_value.cpu().numpy(), res.active_mask.cpu().numpy()
+                for b in range(B):
+                    r = orc.least_squares(
+                        lambda x, yb: model(x) - yb, x0,
+                        jac=lambda x, yb: A + 0.3 * np.cos(Bm @ x)[:, None] * Bm,
+                        bounds=(lb, ub), method=method, scaling=scaling, args=(y[b],))
+                    total += 1
+                    assert abs(ob[b] - r.obj_value) <= 1e-8 * r.obj_value + 1e-18, \
+                        (n, method, scaling, b)
+                    exact += (st[b] == r.status and nf[b] == r.nfev and
+                              np.allclose(X[b], r.x, rtol=1e-8, atol=1e-9) and
+                              np.array_equal(mk[b], np.asarray(r.active_mask)))
+    assert exact >= 0.99 * total, (exact, total)
+    return dict(total=total, exact=exact)
+
+
+def check_random_tall_vs_oracle(lib, dev, seed=7):
+    """Tall mode (n > 8, odd and even) on random bounded nonlinear problems
+    against the oracle: status, counters, active set equal, x / cost 1e-8."""
+    from oracle import blsq_oracle as orc
+    rng = np.random.default_rng(seed)
+    out = {}
+    for n in (9, 13, 20, 33):
+        for method in ("trf", "dogbox"):
+            m = int(rng.integers(3 * n, 6 * n))
+            A = rng.standard_normal((m, n))
+            Bm = rng.standard_normal((m, n)) * 0.3
+            xt = rng.uniform(-1, 1, n)
+
+            def model(x):
+                return A @ x + 0.3 * np.sin(Bm @ x)
+            y = model(xt) + 0.01 * rng.standard_normal(m)
+            lb, ub, x0 = np.full(n, -0.6), np.full(n, 0.7), np.full(n, 0.05)
+            At, Bt, yt = T(A, dev), T(Bm, dev), T(y, dev)
+            ref = orc.least_squares(lambda x: model(x) - y, x0,
+                                    jac=lambda x: A + 0.3 * np.cos(Bm @ x)[:, None] * Bm,
+                                    bounds=(lb, ub), method=method)
+            res = least_squares(lambda x: At @ x + 0.3 * torch.sin(Bt @ x) - yt, T(x0, dev),
+                                jac=lambda x: At + 0.3 * torch.cos(Bt @ x)[:, None] * Bt,
+                                bounds=(T(lb, dev), T(ub, dev)), method=method, _lib=lib)
+            x = res.x.cpu().numpy()
+            key = (n, method)
+            out[key] = (res.status, res.nfev, int(np.count_nonzero(ref.active_mask)))
+            assert res.status == ref.status and res.nfev == ref.nfev, (key, res.nfev, ref.nfev)
+            assert np.allclose(x, ref.x, rtol=1e-8, atol=1e-9), key
+            assert abs(res.obj_value - ref.obj_value) <= 1e-8 * ref.obj_value, key
+            assert bits(res.active_mask.cpu().numpy(),
+                        np.asarray(ref.active_mask, dtype=np.int64)), key
+    return out

@@ -75,3 +75,11 @@ def test_benchmark_table(lib, tmp_path):
 
 def test_compact_batched(lib):
     cases.check_compact_batched(lib, DEV)
+
+
+def test_random_small_vs_oracle(lib):
+    print(cases.check_random_small_vs_oracle(lib, DEV))
+
+
+def test_random_tall_vs_oracle(lib):
+    print(cases.check_random_tall_vs_oracle(lib, DEV))

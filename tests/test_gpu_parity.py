@@ -211,3 +211,11 @@ def test_benchmark_table(lib, dev, tmp_path):
 
 def test_compact_batched(lib, dev):
     cases.check_compact_batched(lib, dev)
+
+
+def test_random_small_vs_oracle(lib, dev):
+    print(cases.check_random_small_vs_oracle(lib, dev))
+
+
+def test_random_tall_vs_oracle(lib, dev):
+    print(cases.check_random_tall_vs_oracle(lib, dev))
