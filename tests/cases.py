@@ -377,6 +377,13 @@ def check_corpus_single(lib, dev, max_n=8):
             if status > 0 and res.status > 0 and obj > 1e-20:
                 assert abs(res.obj_value - obj) <= 1e-3 * max(obj, 1e-9), \
                     (key, res.obj_value, obj)
+            if name not in CHAOTIC:
+                # finite differences: the callbacks return NumPy's own f, so
+                # the FD Jacobian differs from scipy's by the 1-ulp reciprocal
+                # only; status and nfev still agree almost everywhere
+                stats["fd_total"] = stats.get("fd_total", 0) + 1
+                stats["fd_exact"] = stats.get("fd_exact", 0) + (
+                    res.status == int(status) and res.nfev == int(nfev))
             continue
         assert res.status == int(status), (key, res.status, status)
         assert res.nfev == int(nfev) and res.njev == int(njev), key
@@ -387,6 +394,7 @@ def check_corpus_single(lib, dev, max_n=8):
         # zero-residual problems end at obj ~ 1e-30: absolute floor 1e-18
         assert abs(res.obj_value - obj) <= 1e-8 * obj + 1e-18, key
         stats["exact_status"] += 1
+    assert stats.get("fd_exact", 0) >= 0.95 * stats.get("fd_total", 0), stats
     return stats
 
 
