@@ -137,7 +137,19 @@ struct GramLayout {
     static constexpr int NBLK = Tri<NB>::COUNT;
     // Blocks per role.  In pass 2 role 0 also accumulates Y^T f and J^T f
     // (2 NB DFMAs per chunk = NB/4 DMMAs of pipe time), so it gets fewer blocks.
-    static constexpr int ROLES = (PASS == 2) ? C::R2 : C::R1;
+    // SPLIT: the Gram blocks are divided over SPLIT CTAs (consecutive
+    // blockIdx.x) that stream the same tiles.  At n = 256 the upper half of
+    // the Gram matrix is 263 KB of accumulators -- more than the register file
+    // of one SM -- so one CTA cannot hold it without spilling; two CTAs hold
+    // 33-34 blocks per warp each and J is read twice (it is compute bound by
+    // 5x).  Pass 1 only: measured 8.7 -> 2.2 ms per 2^20 rows (85 % of the
+    // FP64 peak on the executed blocks); in pass 2 both CTAs would have to
+    // repeat the whole Y = J R1^-1 product, which dominates it (43.7 -> 59.6
+    // ms), so pass 2 stays one CTA until Y can be shared through a cluster.
+    // ROLES_CTA = roles inside one CTA, ROLES = roles over the block list.
+    static constexpr int SPLIT = (NB >= 32 && PASS == 1) ? 2 : 1;
+    static constexpr int ROLES_CTA = (PASS == 2) ? C::R2 : C::R1;
+    static constexpr int ROLES = ROLES_CTA * SPLIT;
     static constexpr int FW = (PASS == 2) ? (NB + 3) / 4 : 0;
     static constexpr int B0_ = (NBLK + FW) / ROLES - FW;
     static constexpr int B0 = (ROLES == 1) ? NBLK : (B0_ < 1 ? 1 : B0_);         // role 0
@@ -152,7 +164,7 @@ struct GramLayout {
                                                                               : NBLK - role_begin(r)));
     }
     static constexpr int MAXQ = B0 > BPR ? B0 : BPR;
-    static constexpr int KS = C::CW / ROLES;                       // row split
+    static constexpr int KS = C::CW / ROLES_CTA;                   // row split
     static constexpr int THREADS = (C::CW + 1) * 32;
     static constexpr int S = (PASS == 2) ? C::S2 : C::S1;          // ring stages
     static constexpr int STAGE_DOUBLES = 4 * QS + C::T;            // tile + f (pass 2)
@@ -201,8 +213,9 @@ __device__ __forceinline__ void consumer_loop(int64_t njobs, const double* __res
     constexpr int NQ = L::role_count(ROLE);
     static_assert(NQ > 0, "every role must own at least one Gram block");
     constexpr int KS = L::KS;
+    constexpr int KU = (NB >= 32) ? 1 : 2;      // two k-chunks of fragments do not fit at NB = 32
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int ks = warp / L::ROLES;
+    const int ks = warp / L::ROLES_CTA;
     const int lr = lane >> 2, lc = lane & 3;
     const int RS = EXACT ? W : n;               // row stride inside a quarter
 
@@ -220,7 +233,7 @@ __device__ __forceinline__ void consumer_loop(int64_t njobs, const double* __res
 
     int stage = 0;
     uint32_t phase = 0;
-    for (int64_t t = blockIdx.x; t < njobs; t += gridDim.x) {
+    for (int64_t t = blockIdx.x / L::SPLIT; t < njobs; t += gridDim.x / L::SPLIT) {
         mbar_wait(&full[stage], phase);
         const double* tj = smem + (size_t)stage * L::STAGE_DOUBLES;
         const double* tf = tj + 4 * QS;
@@ -294,7 +307,7 @@ __device__ __forceinline__ void consumer_loop(int64_t njobs, const double* __res
         // ---- phase B: G += src^T src; chunk kc = row kc of the four quarters ----
         const double* src = (PASS == 2) ? ybuf : tj;
         const int SRS = (PASS == 2) ? W : RS;
-#pragma unroll 2
+#pragma unroll KU
         for (int kc = ks; kc < QR; kc += KS) {
             const double* base = src + lc * QS + kc * SRS + lr;
             double frag[NB];
@@ -424,7 +437,7 @@ gram_kernel(int64_t m, int n, const double* __restrict__ J, const double* __rest
         int stage = 0;
         uint32_t phase = 0;
         const uint32_t q_bytes = (uint32_t)(QR * n) * 8u;
-        for (int64_t job = blockIdx.x; job < njobs; job += gridDim.x) {
+        for (int64_t job = blockIdx.x / L::SPLIT; job < njobs; job += gridDim.x / L::SPLIT) {
             mbar_wait(&empty[stage], phase ^ 1);
             const int64_t t = (PASS == 1) ? sample_tile(job, sstride) : job;
             const int64_t row0 = t * T;
@@ -453,7 +466,8 @@ gram_kernel(int64_t m, int n, const double* __restrict__ J, const double* __rest
             if (++stage == S) { stage = 0; phase ^= 1; }
         }
     } else {
-        consumer_dispatch<NB, PASS, EXACT>(warp % L::ROLES, njobs, rinvp_g, n, smem, full, empty, rec,
+        consumer_dispatch<NB, PASS, EXACT>((blockIdx.x % L::SPLIT) * L::ROLES_CTA + warp % L::ROLES_CTA,
+                                           njobs, rinvp_g, n, smem, full, empty, rec,
                                            std::make_integer_sequence<int, L::ROLES>{});
     }
     if (L::KS > 1) {
@@ -550,7 +564,10 @@ int launch_gram_e(int64_t m, int n, const double* J, const double* f, const doub
     const int sms = sm_count();
     int64_t ntiles = (m + C::T - 1) / C::T;
     if (PASS == 1 && sstride > 1) ntiles /= sstride;
-    int grid = (int)(ntiles < sms ? (ntiles > 0 ? ntiles : 1) : sms);
+    int64_t want = (ntiles > 0 ? ntiles : 1) * L::SPLIT;       // SPLIT CTAs per tile stream
+    int grid = (int)(want < sms ? want : sms);
+    grid -= grid % L::SPLIT;
+    if (grid < L::SPLIT) grid = L::SPLIT;
     cudaError_t e = cudaFuncSetAttribute(gram_kernel<NB, PASS, EXACT>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)L::SMEM_BYTES);
