@@ -180,7 +180,7 @@ int blsq_compact_batched(int64_t A, const int32_t* idx, const int32_t* istate, i
                          int32_t* work, void* stream);
 
 
-/* ---- tall mode: one problem, m_local rows on this rank, n even, n <= 256 --
+/* ---- tall mode: one problem, m_local rows on this rank, 2 <= n <= 256 -----
  *
  * Per Jacobian evaluation (trf.py:244,264-274; dogbox.py:170,197-199) the
  * rank runs a preconditioned Cholesky QR on [J | f]:
