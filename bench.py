@@ -97,22 +97,63 @@ def _cpu_worker(job):
     return count, nfev, time.perf_counter() - t0, res
 
 
-def cpu_fits_per_second(w, per_core, cores=None, seed0=1000):
-    """Oracle (NumPy port of the reference) over all host cores."""
+def _cpu_worker_init():
+    # one BLAS thread per worker process: the fits are tiny (68 x 4 SVDs) and
+    # the parallelism is over problems.  (Environment variables would have to
+    # be set before numpy is imported; threadpoolctl works at any time.)
+    try:
+        from threadpoolctl import threadpool_limits
+        _cpu_worker_init.limit = threadpool_limits(limits=1)
+    except Exception:
+        pass
+    from oracle import blsq_oracle  # noqa: F401
+
+
+_CPU_POOL = {}
+
+
+def _close_cpu_pools():
+    for pool in _CPU_POOL.values():
+        pool.terminate()
+        pool.join()
+    _CPU_POOL.clear()
+
+
+import atexit  # noqa: E402
+atexit.register(_close_cpu_pools)
+
+
+def _cpu_pool(cores):
+    """ONE worker pool per process, created and warmed outside every timed
+    region.  The parent imports the model module (and with it torch) before
+    the fork, so no worker pays an import inside a measurement."""
     import multiprocessing as mp
+    pool = _CPU_POOL.get(cores)
+    if pool is None:
+        from oracle import blsq_oracle  # noqa: F401
+        from bounded_lsq_b200 import synthetic  # noqa: F401
+        pool = mp.get_context("fork").Pool(cores, initializer=_cpu_worker_init)
+        _CPU_POOL[cores] = pool
+        # warm-up: every worker solves a few fits
+        pool.map(_cpu_worker, [("ExpDecay2", "trf", "exact", 1, 2)] * (2 * cores))
+    return pool
+
+
+def cpu_fits_per_second(w, per_core, cores=None, seed0=1000):
+    """Oracle (NumPy port of the reference) over all host cores; the timed
+    region is the pool.map over the jobs and nothing else."""
     cores = cores or os.cpu_count() or 1
-    os.environ.setdefault("OMP_NUM_THREADS", "1")
-    os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
-    jobs = [(w["model"], w["method"], w["jac"], seed0 + c, per_core)
-            for c in range(cores)]
-    ctx = mp.get_context("fork")
+    pool = _cpu_pool(cores)
+    # two jobs per core: a core that finishes early picks up another one
+    half = max(1, per_core // 2)
+    jobs = [(w["model"], w["method"], w["jac"], seed0 + c, half)
+            for c in range(2 * cores)]
     t0 = time.perf_counter()
-    with ctx.Pool(cores) as pool:
-        out = pool.map(_cpu_worker, jobs)
+    out = pool.map(_cpu_worker, jobs, chunksize=1)
     wall = time.perf_counter() - t0
     fits = sum(o[0] for o in out)
     cpu_fits_per_second.last = dict(
-        seeds=[j[3] for j in jobs], per_core=per_core,
+        seeds=[j[3] for j in jobs], per_core=half,
         results=[r for o in out for r in o[3]])
     return fits / wall, cores, fits, sum(o[1] for o in out) / fits
 
@@ -149,25 +190,37 @@ def gpu_parity_of_cpu_sample(w, fun, jac, lb, ub, dev):
     }
 
 
+def static_config(w, B, chunk, callbacks=None):
+    """The workload description both arms print (run-dependent values are
+    added to it by the arm that measured them)."""
+    c = {"workload": w["desc"], "problems_per_gpu": B, "chunk": chunk,
+         "method": w["method"], "jac": w["jac"], "n": w["n"], "m": w["m"]}
+    if callbacks is not None:
+        c["callbacks"] = callbacks
+    return c
+
+
 def run_reference_arm(args, w):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    # a step is a bounded sample: ~6 s of CPU work per core, so that pool
-    # start-up (fork + imports) stays a small part of the timed region
+    # a step is a bounded sample: ~1 s of CPU work per core (C2: 360 fits/s/
+    # core, SURVEY section 6), the whole --steps K run a few minutes at most
     per_core = 256 if w["jac"] == "exact" else 96
-    for _ in range(min(args.warmup, 1)):
-        cpu_fits_per_second(w, 4, cores)
-    t0 = time.perf_counter()
+    _cpu_pool(cores)
+    for _ in range(min(args.warmup, 2)):
+        cpu_fits_per_second(w, 16, cores)
     fits = 0
     nfev = 0.0
+    wall = 0.0
     for k in range(args.steps):
         v, c, f, nf = cpu_fits_per_second(w, per_core, cores, seed0=2000 + 97 * k)
         fits += f
         nfev += nf * f
-    wall = time.perf_counter() - t0
+        wall += f / v
     value = fits / wall
+    B = args.batch or w["B"]
     line = {
         "impl": "reference", "metric": "bounded fits solved/sec (batched)",
         "value": value, "unit": "fits/s", "n_gpus": args.gpus,
@@ -175,18 +228,23 @@ def run_reference_arm(args, w):
         "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": w["desc"], "sample_fits_per_step": per_core * cores},
+        "config": dict(static_config(w, B, min(B, w.get("chunk", B))),
+                       sample_fits_per_step=fits // max(args.steps, 1),
+                       fits_per_second_per_core=value / cores),
         "cpu_baseline": {"value": value, "unit": "fits/s", "cores": cores,
                          "kind": "port",
-                         "sample": f"{per_core} fits per core x {cores} cores "
-                                   f"per step, oracle/blsq_oracle.py "
-                                   f"(NumPy/SciPy restatement of the "
-                                   f"reference), mean nfev {nfev / fits:.1f}"},
+                         "sample": f"{fits // max(args.steps, 1)} fits per step "
+                                   f"over {cores} worker processes (pool created "
+                                   f"and warmed before the timed region), "
+                                   f"oracle/blsq_oracle.py (NumPy/SciPy restatement "
+                                   f"of the reference, bit-identical to it on the "
+                                   f"golden files), mean nfev {nfev / fits:.1f}"},
         "e2e": {"value": value, "unit": "fits/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
     }
     if args.workload == "c2" and not args.no_tall and args.batch is None:
         line["tall"] = run_tall_reference_arm(args, WORKLOADS["c4"], standalone=False)
+        line["config"]["tall_value"] = line["tall"]["value"]
     print(json.dumps(line))
 
 
@@ -368,10 +426,11 @@ def run_tall_reference_arm(args, w, standalone=True):
     return line
 
 
-def run_tall(args, w, standalone=True):
+def run_tall(args, w, standalone=True, light=False):
     """Tall workload.  standalone: own process-group set-up and JSON line;
     otherwise called from the batched main (default run) which attaches the
-    returned dict to its line as "tall"."""
+    returned dict to its line as "tall".  light: value only (no e2e, no CPU
+    baseline) -- the asymmetric-start companion record."""
     import torch
     import torch.distributed as dist
     from bounded_lsq_b200 import least_squares
@@ -387,7 +446,8 @@ def run_tall(args, w, standalone=True):
     n = w["n"]
     m_total = args.rows or w["m"]
     rows = m_total // world                      # "strong": total rows fixed
-    wl = TallLinExpDevice(rows, n, dev, seed=rank, lb=w.get("lb", -0.5))
+    kw = dict(x0_tail=w["x0_tail"]) if w.get("x0_tail") else {}
+    wl = TallLinExpDevice(rows, n, dev, seed=rank, lb=w.get("lb", -0.5), **kw)
     if args.method:
         w = dict(w, method=args.method)
     x0 = torch.as_tensor(wl.x0, device=dev)
@@ -454,7 +514,7 @@ def run_tall(args, w, standalone=True):
     # end to end: the problem data comes from pinned host memory every step
     # (skipped for C5: 8 x 25 GB of pinned host memory)
     its_e2e, e2e_ms, h2d = 0, None, 0
-    if not w.get("no_e2e"):
+    if not w.get("no_e2e") and not light:
         A_h = wl.A_t.cpu().pin_memory()
         t_h = wl.t_t.cpu().pin_memory()
         y_h = wl.y_t.cpu().pin_memory()
@@ -481,7 +541,7 @@ def run_tall(args, w, standalone=True):
         return None
 
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and not light:
         m_cpu = min(m_total, 1 << 19)
         v, dt, it = tall_cpu_iterations_per_second(n, m_cpu, 4)
         cpu = {"value": v * m_cpu / m_total, "unit": "iterations/s",
@@ -501,6 +561,11 @@ def run_tall(args, w, standalone=True):
         "config": {"workload": w["desc"], "rows_total": m_total,
                    "rows_per_gpu": rows, "n": n, "method": w["method"],
                    "callbacks": args.callbacks,
+                   "x0_tail": list(w["x0_tail"]) if w.get("x0_tail") else
+                   "SURVEY 8(d) start [.5, 1, .5, 1]: identical exponentials, "
+                   "J(x0) exactly rank deficient, ulp-chaotic for TRF in the "
+                   "reference itself; full parity is demonstrated on the "
+                   "asymmetric start (tall_asymmetric_start)",
                    "step": "one complete TRF solve from x0; an iteration = one "
                            "accepted step (Jacobian + CholeskyQR2 + its trials)",
                    "iterations_per_step": its / args.steps,
@@ -575,9 +640,6 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from bounded_lsq_b200 import least_squares_batched, PerProblem
-    from bounded_lsq_b200 import batched as drv
-
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -586,8 +648,55 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
+    line = run_batched(args, w, args.workload, args.steps, args.warmup,
+                       args.batch or w["B"], cpu_baseline=not args.no_cpu_baseline)
+
+    # the other half of BASELINE.json's metric (TRF iterations/s at m=16M,
+    # n=64) rides along on the default run as the "tall" object, and a short
+    # run of configs[2] (C3: dogbox, 2-point Jacobian; ONE 1M-problem chunk of
+    # the 10M) as "c3".  Their headline numbers are repeated inside `config`.
+    if args.workload == "c2" and not args.no_tall and args.batch is None:
+        torch.cuda.empty_cache()
+        tall_line = run_tall(args, WORKLOADS["c4"], standalone=False)
+        torch.cuda.empty_cache()
+        tall_asym = run_tall(args, dict(WORKLOADS["c4"], x0_tail=(0.8, 1.5, 0.3, 4.0)),
+                             standalone=False, light=True)
+        torch.cuda.empty_cache()
+        c3_line = run_batched(args, WORKLOADS["c3"], "c3", max(2, args.steps // 4),
+                              max(1, min(args.warmup, 2)), 1_000_000,
+                              cpu_baseline=False)
+        if rank == 0:
+            line["tall"] = tall_line
+            line["tall_asymmetric_start"] = tall_asym
+            line["c3"] = c3_line
+            cfg = line["config"]
+            cfg["tall_value_it_per_s"] = tall_line["value"]
+            cfg["tall_roofline_frac"] = tall_line["roofline"]["frac"]
+            cfg["tall_e2e_it_per_s"] = (tall_line["e2e"] or {}).get("value")
+            cfg["tall_asym_value_it_per_s"] = tall_asym["value"]
+            cfg["c3_value_fits_per_s"] = c3_line["value"]
+            cfg["c3_roofline_frac"] = c3_line["roofline"]["frac"]
+            cfg["c3_e2e_fits_per_s"] = c3_line["e2e"]["value"]
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_batched(args, w, wname, steps, warmup, B, cpu_baseline=True):
+    """One batched workload on this rank's GPU (problems split by index over
+    the ranks, no collective on the data path); returns the JSON record on
+    rank 0, None elsewhere."""
+    import torch
+    import torch.distributed as dist
+    from bounded_lsq_b200 import least_squares_batched, PerProblem
+    from bounded_lsq_b200 import batched as drv
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dev = torch.device("cuda", local)
     model = _model(w["model"])
-    B = args.batch or w["B"]            # per GPU ("weak")
     chunk = min(B, w.get("chunk", B))
     n, m = w["n"], w["m"]
     method = w["method"]
@@ -655,7 +764,7 @@ def main():
         return float(t.item())
 
     # ---- device-resident timing -----------------------------------------
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         solve(y_dev, x0_dev)
     barrier()
     launches = 0
@@ -665,14 +774,14 @@ def main():
         e1 = torch.cuda.Event(enable_timing=True)
         barrier()
         e0.record()
-        for _ in range(args.steps):
+        for _ in range(steps):
             outs = solve(y_dev, x0_dev)
             launches += sum(o.kernel_launches for o in outs)
             rounds += sum(o.rounds for o in outs)
         e1.record()
         barrier()
     dev_ms = reduce_max(e0.elapsed_time(e1))
-    value = world * B * args.steps / (dev_ms * 1e-3)
+    value = world * B * steps / (dev_ms * 1e-3)
     status = torch.cat([o.status for o in outs])
     nfev_mean = float(torch.cat([o.nfev for o in outs]).double().mean())
     njev_mean = float(torch.cat([o.njev for o in outs]).double().mean())
@@ -700,7 +809,7 @@ def main():
     e3 = torch.cuda.Event(enable_timing=True)
     t_wall0 = time.perf_counter()
     e2.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         outs = solve(y_host, x0_host)
         x_out.copy_(torch.cat([o.x for o in outs]), non_blocking=True)
         st_out.copy_(torch.cat([o.status for o in outs]), non_blocking=True)
@@ -709,22 +818,13 @@ def main():
     e3.record()
     barrier()
     e2e_ms = reduce_max(e2.elapsed_time(e3))
-    e2e_value = world * B * args.steps / (e2e_ms * 1e-3)
+    e2e_value = world * B * steps / (e2e_ms * 1e-3)
     h2d = y_host.numel() * 8 + x0_host.numel() * 8
     d2h = x_out.numel() * 8 + st_out.numel() * 8 + obj_out.numel() * 8
 
-    # the other half of BASELINE.json's metric (TRF iterations/s at m=16M,
-    # n=64) rides along on the default run as the "tall" object
-    tall_line = None
-    if args.workload == "c2" and not args.no_tall and args.batch is None:
-        del y_dev, x0_dev, outs, y_host, x0_host
-        torch.cuda.empty_cache()
-        tall_line = run_tall(args, WORKLOADS["c4"], standalone=False)
-
+    del y_dev, x0_dev, outs, y_host, x0_host
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        return None
 
     peaks = {}
     try:
@@ -741,8 +841,8 @@ def main():
         "bound": "hbm", "kernel": "lin_kernel (blsq_linearise_batched)",
         "achieved": lin.get("gbs"), "peak": peak, "unit": "GB/s",
         "frac": (lin.get("gbs") / peak) if lin.get("gbs") else None,
-        "traffic": (_ncu_traffic(args.workload) or {}).get("bytes_per_launch"),
-        "traffic_source": _ncu_traffic(args.workload), "peak_source": peak_src,
+        "traffic": (_ncu_traffic(wname) or {}).get("bytes_per_launch"),
+        "traffic_source": _ncu_traffic(wname), "peak_source": peak_src,
         "algorithmic_bytes_per_problem": lin.get("bytes_per_problem"),
         "avg_launch_ms": lin.get("avg_ms"), "launches": lin.get("launches"),
         "share_of_kernel_time": lin.get("share"),
@@ -757,9 +857,19 @@ def main():
         "callbacks_ms_per_step": ksum.get("callbacks_ms"),
         "kernels_ms_per_step": ksum.get("kernels_ms"),
     }
+    # step level: SURVEY 8(d) algorithmic bytes of the WHOLE solve
+    # (sum over problems of njev*8m(n+1) + nfev*(8m+32n)) over the device time
+    # of a step -- callbacks, every kernel, launch gaps and host look-ups
+    # included -- against the same HBM peak
+    step_bytes = B * (njev_mean * 8 * m * (n + 1) + nfev_mean * (8 * m + 32 * n))
+    roofline["step_algorithmic_bytes"] = step_bytes
+    roofline["step_frac"] = step_bytes / (dev_ms / steps * 1e-3) / 1e9 / peak
+    if ksum.get("kernels_ms"):
+        roofline["step_frac_kernels_only"] = \
+            step_bytes / (ksum["kernels_ms"] * 1e-3) / 1e9 / peak
 
     cpu = None
-    if not args.no_cpu_baseline:
+    if cpu_baseline:
         per_core = 48 if w["jac"] == "exact" else 24
         v, cores, fits, nf = cpu_fits_per_second(w, per_core)
         cpu = {"value": v, "unit": "fits/s", "cores": cores, "kind": "port",
@@ -772,31 +882,29 @@ def main():
 
     line = {
         "metric": "bounded fits solved/sec (batched)", "value": value,
-        "unit": "fits/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
+        "unit": "fits/s", "n_gpus": world, "steps": steps,
+        "warmup": warmup, "ms_per_step": dev_ms / steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": w["desc"], "problems_per_gpu": B,
-                   "chunk": chunk, "method": method, "jac": w["jac"],
-                   "callbacks": args.callbacks, "n": n, "m": m,
-                   "l2": "inputs (J+f per round: %.1f GB) exceed the 126 MB L2"
-                         % (B * m * (n + 1) * 8 / 1e9),
-                   "mean_nfev": nfev_mean, "mean_njev": njev_mean,
-                   "converged_frac": converged,
-                   "rounds_per_step": rounds / args.steps},
+        "config": dict(
+            static_config(w, B, chunk, args.callbacks),
+            l2="inputs (J+f per round: %.1f GB) exceed the 126 MB L2"
+               % (chunk * m * (n + 1) * 8 / 1e9),
+            data_pool="%d distinct seeded problems per GPU tiled to %d "
+                      "(same traffic; host generation time)" % (ngen, B),
+            mean_nfev=nfev_mean, mean_njev=njev_mean, converged_frac=converged,
+            rounds_per_step=rounds / steps),
         "e2e": {"value": e2e_value, "unit": "fits/s",
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": e2e_ms / args.steps},
+                "ms_per_step": e2e_ms / steps},
         "gpu_launches": launches,
         "roofline": roofline,
         "cpu_baseline": cpu,
         "clocks": clk.summary(),
     }
-    if tall_line is not None:
-        line["tall"] = tall_line
-    print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    return line
+
+
 
 
 if __name__ == "__main__":

@@ -107,6 +107,23 @@ class Lib:
             self._fn[name] = f
 
     # -- plumbing ----------------------------------------------------------
+    def device_guard(self, ref):
+        """Context manager that makes ``ref``'s device the CUDA current device:
+        the kernels are launched on the current device, so it must be the one
+        that owns the pointers and the stream (a solve on cuda:1 while cuda:0
+        is current would otherwise launch on GPU 0 with GPU 1's memory)."""
+        if isinstance(ref, torch.Tensor) and ref.is_cuda:
+            return torch.cuda.device(ref.device)
+        import contextlib
+        return contextlib.nullcontext()
+
+    def same_device(self, ref, **tensors):
+        for name, t in tensors.items():
+            if isinstance(t, torch.Tensor) and t.device != ref.device:
+                raise BlsqError(f"`{name}` is on {t.device} but `x0` is on "
+                                f"{ref.device}: all tensors of a solve must "
+                                "live on one device")
+
     def stream(self, ref):
         if ref.is_cuda:
             return torch.cuda.current_stream(ref.device).cuda_stream

@@ -458,13 +458,24 @@ def solve_batched(lib, method, fun, jac, X0, lb, ub, ftol, xtol, gtol,
     status = istate[:, 0].to(torch.int64)
     bad = status < L.STATUS_RUNNING
     if bool(bad.any().item()):
-        code = int(status[bad][0].item())
-        # trust_region.py:28-35 raises these from inside trf
-        if code == L.STATUS_ERR_TR_ZERO:
-            raise ValueError("`s` is zero.")
-        if code == L.STATUS_ERR_TR_OUTSIDE:
-            raise ValueError("`x` is not within the trust region.")
-        raise RuntimeError(f"internal status {code}")
+        # trust_region.py:28-35 raises these from inside trf.  One problem:
+        # the same exception.  A batch: the other B - 1 fits are valid, so the
+        # failing ones keep their negative status (success = False) and the
+        # caller is told which they are.
+        which = torch.nonzero(bad).view(-1)
+        code = int(status[which[0]].item())
+        if B == 1:
+            if code == L.STATUS_ERR_TR_ZERO:
+                raise ValueError("`s` is zero.")
+            if code == L.STATUS_ERR_TR_OUTSIDE:
+                raise ValueError("`x` is not within the trust region.")
+            raise RuntimeError(f"internal status {code}")
+        warnings.warn(
+            "bounded_lsq_b200: %d of %d problems stopped where the reference "
+            "raises ValueError from intersect_trust_region (status %d = `s` is "
+            "zero, %d = `x` is not within the trust region); first indices %s"
+            % (which.numel(), B, L.STATUS_ERR_TR_ZERO, L.STATUS_ERR_TR_OUTSIDE,
+               which[:8].tolist()), RuntimeWarning)
 
     x = state[:, lay["x"]:lay["x"] + n].contiguous()
     if method == "trf":

@@ -177,7 +177,8 @@ BLSQ_HD void phi_and_derivative(double alpha, const double* suf,
 template <int N>
 BLSQ_HD void solve_lsq_trust_region(int m, const double* suf, const double* s,
                                     const double* Vt, double Delta,
-                                    double& alpha, double* p) {
+                                    double& alpha, double* p,
+                                    bool zero_col = true) {
     double smin = s[0], smax = s[0];
     BLSQ_UNROLL
     for (int i = 1; i < N; i++) {
@@ -221,6 +222,17 @@ BLSQ_HD void solve_lsq_trust_region(int m, const double* suf, const double* s,
         double cand = alpha - q;
         lo = lo > cand ? lo : cand;
         alpha -= (phi + Delta) * q / Delta;
+    }
+    // An EXACTLY zero singular value of a matrix WITHOUT a zero column
+    // (duplicate columns: the Gram-Schmidt / Jacobi route keeps the zero LAPACK
+    // would return as ~1e-16 s_max) makes |p(alpha)| < Delta for every
+    // alpha > 0: no root, and the iteration above can leave alpha negative.
+    // The reference never sees this (its noise-level s_min gives the root a
+    // bracket); take the minimum-norm end of the bracket.  A zero COLUMN
+    // (Beale at x0) gives the reference an exact zero too and is left alone.
+    if (smin == 0.0 && !zero_col && !(alpha > 0.0)) {
+        double a1 = 0.001 * hi, a2 = sqrt(lo * hi);
+        alpha = a1 > a2 ? a1 : a2;
     }
     BLSQ_UNROLL
     for (int j = 0; j < N; j++) w[j] = suf[j] / (s[j] * s[j] + alpha);
@@ -737,9 +749,19 @@ BLSQ_HD int trf_round_impl(double* st, int* ist, const double* lin,
         } else if (MODE == 1) {
             return TRF_DEFER;
         } else {
+            // does the hat-space matrix have an exactly zero column?
+            bool zero_col = false;
+            BLSQ_UNROLL
+            for (int j = 0; j < N; j++) {
+                bool z = true;
+                BLSQ_UNROLL
+                for (int i = 0; i < N; i++)
+                    if (i <= j) z = z && (A[i * N + j] == 0.0);
+                zero_col = zero_col || z;
+            }
             double s[N], Vt[N * N], suf[N];
             hat_finish<N>(A, b, s, Vt, suf);
-            solve_lsq_trust_region<N>(P.m, suf, s, Vt, Delta, alpha, p_h);
+            solve_lsq_trust_region<N>(P.m, suf, s, Vt, Delta, alpha, p_h, zero_col);
         }
     }
     st[S::ALPHA] = alpha;

@@ -647,7 +647,8 @@ BLSQ_HD void tall_phi(const Blk& B, int n, double alpha, const double* suf, cons
 
 // trust_region.py:56-152; S, SUF, VT from tall_hat_svd.  p_h -> W.p_h.
 BLSQ_HD void tall_solve_tr(const Blk& B, const TallWork& W, double m, const double* S,
-                           const double* SUF, const double* VT, double Delta, double& alpha) {
+                           const double* SUF, const double* VT, double Delta, double& alpha,
+                           bool zero_col) {
     const int n = W.n;
     double smin = dinf(), smax = -dinf();
     for (int i = B.tid; i < n; i += B.nt) {
@@ -688,6 +689,11 @@ BLSQ_HD void tall_solve_tr(const Blk& B, const TallWork& W, double m, const doub
         const double cand = alpha - q;
         lo = lo > cand ? lo : cand;
         alpha -= (phi + Delta) * q / Delta;
+    }
+    // exactly zero singular value: see solve_lsq_trust_region in blsq_core.cuh
+    if (smin == 0.0 && !zero_col && !(alpha > 0.0)) {
+        const double a1 = 0.001 * hi, a2 = sqrt(lo * hi);
+        alpha = a1 > a2 ? a1 : a2;
     }
     B.sync();
     for (int j = B.tid; j < n; j += B.nt) W.w[j] = SUF[j] / (S[j] * S[j] + alpha);
@@ -926,7 +932,20 @@ BLSQ_HD void tall_trf_propose(const Blk& B, const TallParams& P, const TallWork&
     double theta = 1.0 - g_norm;
     if (theta < 0.995) theta = 0.995;
     B.sync();
-    if (!took_gn) tall_solve_tr(B, W, P.m, S, SUF, VT, Delta, alpha);
+    if (!took_gn) {
+        // exactly zero column of [R diag(d); diag(sqrt(diag_h))]?  (see
+        // solve_lsq_trust_region in blsq_core.cuh)
+        bool zc = false;
+        for (int j = B.tid; j < n; j += B.nt) {
+            if (W.diag_h[j] != 0.0) continue;
+            bool z = true;
+            if (W.d[j] != 0.0)
+                for (int i = 0; i <= j && z; i++) z = R[(size_t)i * n + j] == 0.0;
+            zc = zc || z;
+        }
+        const bool zero_col = blk_any(B, zc);
+        tall_solve_tr(B, W, P.m, S, SUF, VT, Delta, alpha, zero_col);
+    }
     B.sync();
     for (int i = B.tid; i < n; i += B.nt) W.p[i] = W.d[i] * W.p_h[i];
     B.sync();

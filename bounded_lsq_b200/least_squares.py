@@ -141,9 +141,28 @@ def least_squares_batched(fun, x0, jac='2-point', bounds=(-float('inf'), float('
     lib = _lib if _lib is not None else L.get_lib()
     _validate_common(method, bounds, jac)
     options = dict(options)
+    # the target device: x0's, or options['device'] for host inputs
+    if isinstance(x0, torch.Tensor) and x0.is_cuda:
+        target = x0.device
+    elif lib.requires_cuda:
+        target = torch.device(options.get("device") or _default_device())
+    else:
+        target = None
+    guard = torch.cuda.device(target) if target is not None else \
+        lib.device_guard(None)
+    with guard:
+        return _least_squares_batched(lib, fun, x0, jac, bounds, method, ftol, xtol,
+                                      gtol, max_nfev, scaling, diff_step, args,
+                                      kwargs, options)
+
+
+def _least_squares_batched(lib, fun, x0, jac, bounds, method, ftol, xtol, gtol,
+                           max_nfev, scaling, diff_step, args, kwargs, options):
     if not isinstance(x0, torch.Tensor):
         dev = _default_device() if lib.requires_cuda else torch.device("cpu")
         x0 = torch.as_tensor(x0, dtype=torch.float64, device=dev)
+        options.pop("h2d_chunks", None)
+        options.pop("device", None)
     elif lib.requires_cuda and not x0.is_cuda:
         # HOST inputs (x0 and the PerProblem data on the CPU, ideally pinned):
         # they are streamed to the device in chunks and the first rounds of
@@ -151,6 +170,13 @@ def least_squares_batched(fun, x0, jac='2-point', bounds=(-float('inf'), float('
         x0, args, kwargs, plan = _stage_host_inputs(x0, args, kwargs, options)
         if plan is not None and "trace" not in options:
             options["prologue"] = plan
+        elif plan is not None:
+            # not streamed (the trace hook wants whole-batch rounds): the
+            # copies were queued on the side stream, wait for the last one
+            torch.cuda.current_stream(x0.device).wait_event(plan[-1][2])
+    else:
+        options.pop("h2d_chunks", None)
+        options.pop("device", None)
     x0 = x0.to(torch.float64).contiguous()
     if x0.dim() != 2:
         raise ValueError("batched `x0` must be (B, n).")
@@ -169,6 +195,9 @@ def least_squares_batched(fun, x0, jac='2-point', bounds=(-float('inf'), float('
     ftol, xtol, gtol = check_tolerance(ftol, xtol, gtol)
     if not bool(lib.in_bounds(x0, lb, ub).all().item()):
         raise ValueError("`x0` is infeasible.")
+    for v in list(args) + list(dict(kwargs).values()):
+        if isinstance(v, PerProblem):
+            lib.same_device(x0, PerProblem=v.tensor)
 
     cb = BatchedCallbacks(fun, jac, args, kwargs, B)
     jarg = jac if isinstance(jac, str) else cb.j
@@ -177,7 +206,11 @@ def least_squares_batched(fun, x0, jac='2-point', bounds=(-float('inf'), float('
     res = OptimizeResult(out)
     res.fun = cb.f(res.x, None)
     res.x_covariance = None
-    res.message = TERMINATION_MESSAGES
+    # per-problem texts: res.message[int(res.status[b])]
+    res.message = dict(TERMINATION_MESSAGES)
+    res.message[L.STATUS_ERR_TR_ZERO] = "ValueError: `s` is zero."
+    res.message[L.STATUS_ERR_TR_OUTSIDE] = \
+        "ValueError: `x` is not within the trust region."
     res.success = res.status > 0
     return res
 
@@ -273,6 +306,14 @@ def least_squares(fun, x0, jac='2-point', bounds=(-float('inf'), float('inf')),
         dev = x0.device
     else:
         dev = _default_device() if lib.requires_cuda else torch.device("cpu")
+    with lib.device_guard(torch.empty(0, device=dev)):
+        return _least_squares(lib, fun, x0, jac, bounds, method, ftol, xtol, gtol,
+                              max_nfev, scaling, diff_step, args, kwargs, options,
+                              dev)
+
+
+def _least_squares(lib, fun, x0, jac, bounds, method, ftol, xtol, gtol, max_nfev,
+                   scaling, diff_step, args, kwargs, options, dev):
     x0 = _to_f64(x0, dev)
     if x0.dim() == 0:
         x0 = x0.reshape(1)

@@ -137,6 +137,52 @@ class GaussPeak:
                 X[:, 4:5] * t + X[:, 5:6] * t * t - y)
 
 
+# ---------------------------------------------- transcendental-free (FD) ----
+
+class RatPoly5:
+    """Rational model y = (a + b t + c t^2) / (1 + d t + e t^2), 5 parameters.
+
+    Only + - * / : NumPy and torch (one rounding per eager op, same order)
+    return bit-identical residuals, so a finite-difference Jacobian formed on
+    the device can be compared with scipy's to the last bit.  This is the
+    parity model for the 2-point / 3-point paths: with
+    ExpDecay2 / GaussPeak the 1-ulp difference between libm's and CUDA's exp
+    is amplified by 1/h ~ 7e7 and hides what the kernels themselves do."""
+
+    n = 5
+    x0 = np.array([1.0, 0.5, 0.2, 0.3, 0.1])
+    lb = np.array([0.0, -1.0, 0.0, 0.0, 0.05])
+    ub = np.array([3.0, 2.0, 0.25, 1.0, 1.0])
+
+    def __init__(self, m=40):
+        self.m = m
+        self.t = np.linspace(0.0, 3.0, m)
+
+    def make_data(self, B, seed=0, noise=0.01):
+        rng = np.random.default_rng(seed)
+        a = rng.uniform(0.5, 2.5, B)
+        b = rng.uniform(-0.5, 1.5, B)
+        c = rng.uniform(0.0, 0.5, B)        # > ub for about half the problems
+        d = rng.uniform(0.1, 0.8, B)
+        e = rng.uniform(0.0, 0.5, B)        # < lb for a tenth of them
+        truth = np.stack([a, b, c, d, e], axis=1)
+        y = np.stack([self.fun_np(truth[i], 0.0) for i in range(B)])
+        y = y + noise * rng.standard_normal(y.shape)
+        return truth, y
+
+    def fun_np(self, x, y):
+        t = self.t
+        num = x[0] + x[1] * t + x[2] * t * t
+        den = 1.0 + x[3] * t + x[4] * t * t
+        return num / den - y
+
+    def fun_t(self, X, y):
+        t = _dev_const(self, X)
+        num = X[:, 0:1] + X[:, 1:2] * t + X[:, 2:3] * t * t
+        den = 1.0 + X[:, 3:4] * t + X[:, 4:5] * t * t
+        return num / den - y
+
+
 # ------------------------------------------------------------------ C4 ----
 
 class TallLinExp:
@@ -147,7 +193,7 @@ class TallLinExp:
     """
 
     def __init__(self, m, n=64, seed=0, noise=0.01, dtype=np.float64,
-                 x0_tail=(0.5, 1.0, 0.5, 1.0)):
+                 x0_tail=(0.5, 1.0, 0.5, 1.0), lb=-0.5, ub=5.0):
         # the default start has the two exponentials
         # identical: J(x0) is exactly rank deficient and the symmetry is only
         # broken by rounding, so TRF iterates are ulp-chaotic from the ~5th
@@ -162,8 +208,9 @@ class TallLinExp:
                                       [1.0, 2.0, 0.5, 3.0]])
         self.y = self._model(self.x_true) + noise * rng.standard_normal(m)
         self.x0 = np.concatenate([np.full(self.k, 0.1), list(x0_tail)])
-        self.lb = np.full(n, -0.5)
-        self.ub = np.full(n, 5.0)
+        # C5: lb = 0 puts about half of the linear truth values outside the box
+        self.lb = np.full(n, float(lb))
+        self.ub = np.full(n, float(ub))
 
     def _model(self, x):
         k, t = self.k, self.t

@@ -41,7 +41,7 @@ from scipy.optimize._numdiff import approx_derivative  # noqa: E402
 
 from oracle import blsq_oracle as orc      # noqa: E402
 from problems import corpus                # noqa: E402
-from bounded_lsq_b200.synthetic import ExpDecay2, GaussPeak, TallLinExp  # noqa: E402
+from bounded_lsq_b200.synthetic import ExpDecay2, GaussPeak, RatPoly5, TallLinExp  # noqa: E402
 
 SQ = np.finfo(float).eps ** 0.5
 
@@ -408,6 +408,16 @@ def gen_batched(name, wl, method, fd, B, seed):
           f"{np.bincount(status).tolist()} oracle bitwise on {nbit}/{B}")
 
 
+def gen_rat():
+    """SURVEY 8a row a24 with bit-identical inputs: finite-difference solves
+    of a transcendental-free model (only + - * /), so the device residuals are
+    NumPy's to the last bit and every gate of the analytic configs applies."""
+    for k, (method, fd) in enumerate((("trf", "2-point"), ("dogbox", "2-point"),
+                                      ("trf", "3-point"), ("dogbox", "3-point"))):
+        gen_batched(f"rat_{method}_{fd[0]}point.npz", RatPoly5(40), method, fd,
+                    96, seed=10 + k)
+
+
 ASYM_TAIL = (0.8, 1.5, 0.3, 4.0)
 
 
@@ -446,9 +456,54 @@ def gen_tall():
     np.savez_compressed(os.path.join(HERE, "tall.npz"), **out)
 
 
+def gen_c5():
+    """Config C5 family (m x n linear + 2 exponentials, lb = 0 so that about
+    half of the bounds are active at the solution) at sizes the CPU reference
+    finishes in seconds: the parity evidence for the n > 64 tall kernels.
+    e/f/g: asymmetric start (well conditioned path); h: the C5 benchmark
+    start (identical exponentials, exactly rank-deficient Jacobian)."""
+    out = {}
+    metas = []
+    for tag, m, n, seed, tail in (("e", 20000, 256, 5, ASYM_TAIL),
+                                  ("f", 8000, 128, 5, ASYM_TAIL),
+                                  ("g", 12000, 200, 5, ASYM_TAIL),
+                                  ("h", 20000, 256, 5, None)):
+        kw = {} if tail is None else dict(x0_tail=tail)
+        wl = TallLinExp(m, n, seed=seed, lb=0.0, **kw)
+        for method in ("trf", "dogbox"):
+            r, t = ref_solve(method, wl.fun_np, wl.jac_np, wl.x0, wl.lb, wl.ub)
+            o, ot = orc_solve(method, wl.fun_np, wl.jac_np, wl.x0, wl.lb,
+                              wl.ub)
+            bit = results_bitwise(r, t, o, ot)
+            rec = pack_result(r, t, n, 4)
+            pre = f"{tag}_{method}_"
+            for fld in ("x", "mask", "trials"):
+                out[pre + fld] = rec[fld]
+            out[pre + "scalars"] = np.array(
+                [rec["obj"], rec["status"], rec["nfev"], rec["njev"],
+                 rec["optimality"], rec["ntrials"]])
+            metas.append(dict(tag=tag, m=m, n=n, seed=seed, method=method,
+                              lb=0.0,
+                              x0_tail=None if tail is None else list(tail),
+                              bitwise=bit, status=rec["status"],
+                              nfev=rec["nfev"], njev=rec["njev"],
+                              nactive=int(np.count_nonzero(rec["mask"]))))
+            print("c5", metas[-1])
+        out[f"{tag}_y_checksum"] = np.float64(np.sum(wl.y))
+        out[f"{tag}_A_checksum"] = np.float64(np.sum(wl.A))
+    out["meta"] = np.array(json.dumps(metas))
+    np.savez_compressed(os.path.join(HERE, "c5.npz"), **out)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "tall":
         gen_tall()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "c5":
+        gen_c5()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "rat":
+        gen_rat()
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "fd3":
         # SURVEY 8(f) rank 1: jac='3-point' on the C3 model, both methods
@@ -473,3 +528,5 @@ if __name__ == "__main__":
     gen_batched("c3_dogbox_3point.npz", GaussPeak(128), "dogbox", "3-point",
                 48, seed=3)
     gen_tall()
+    gen_c5()
+    gen_rat()

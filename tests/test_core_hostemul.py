@@ -39,6 +39,32 @@ def test_golden_fd_jac(lib, name):
     cases.check_golden_fd_jac(lib, DEV, name)
 
 
+@pytest.mark.parametrize("name", ["rat_trf_2point", "rat_dogbox_2point",
+                                  "rat_trf_3point", "rat_dogbox_3point"])
+def test_golden_fd_exact(lib, name):
+    print(cases.check_golden_fd_exact(lib, DEV, name))
+
+
+def test_fd_linearise_bit_exact(lib):
+    cases.check_fd_linearise_bit_exact(lib, DEV)
+
+
+def test_edge_cases_vs_oracle(lib):
+    print(cases.check_edge_cases_vs_oracle(lib, DEV))
+
+
+def test_tall_edge_cases_vs_oracle(lib):
+    print(cases.check_tall_edge_cases_vs_oracle(lib, DEV))
+
+
+# the C5 family (n = 128 ... 256, half of the bounds active); the n = 256
+# dogbox cases take minutes on the single-threaded host emulation and run on
+# the GPU only
+@pytest.mark.parametrize("tag,method", [("f", "trf"), ("f", "dogbox"), ("e", "trf")])
+def test_c5_golden(lib, tag, method):
+    print(cases.check_tall_golden(lib, DEV, tag, method, file="c5.npz"))
+
+
 def test_compaction_invariance(lib):
     cases.check_compaction_invariance(lib, DEV)
 

@@ -42,6 +42,28 @@ def test_golden_fd_jac(lib, dev, name):
     print(name, s)
 
 
+@pytest.mark.parametrize("name", ["rat_trf_2point", "rat_dogbox_2point",
+                                  "rat_trf_3point", "rat_dogbox_3point"])
+def test_golden_fd_exact(lib, dev, name):
+    """2-point / 3-point paths with bit-identical residuals (RatPoly5)."""
+    print(name, cases.check_golden_fd_exact(lib, dev, name))
+
+
+def test_fd_linearise_bit_exact(lib, dev):
+    """FD quotient kernel vs scipy's approx_derivative, bit for bit."""
+    print(cases.check_fd_linearise_bit_exact(lib, dev))
+
+
+def test_edge_cases_vs_oracle(lib, dev):
+    """m < n, NaN residuals, exactly rank-deficient J (batched kernels)."""
+    print(cases.check_edge_cases_vs_oracle(lib, dev))
+
+
+def test_tall_edge_cases_vs_oracle(lib, dev):
+    """m < n, NaN residuals, kappa = 1e6 ... 1e12 (tall kernels)."""
+    print(cases.check_tall_edge_cases_vs_oracle(lib, dev))
+
+
 def test_compaction_invariance(lib, dev):
     cases.check_compaction_invariance(lib, dev)
 
@@ -160,6 +182,16 @@ def test_tall_golden(lib, dev, tag, method):
     """One tall problem (CholeskyQR2 Gram kernels + the n x n tail kernel)
     against the unmodified reference's trf / dogbox on the same data."""
     print(tag, method, cases.check_tall_golden(lib, dev, tag, method))
+
+
+@pytest.mark.parametrize("tag", ["e", "f", "g", "h"])
+@pytest.mark.parametrize("method", ["trf", "dogbox"])
+def test_c5_golden(lib, dev, tag, method):
+    """Config C5 family at reduced m: n = 256 / 128 / 200, lb = 0 so that
+    about half of the bounds are active at the solution (61 ... 142 active),
+    against the unmodified reference: the parity evidence for the n > 64
+    kernels (split-CTA Gram pass 1, pass 2, Jacobi / QR tails)."""
+    print(tag, method, cases.check_tall_golden(lib, dev, tag, method, file="c5.npz"))
 
 
 def test_tall_factor_matches_qr(lib, dev):
