@@ -181,7 +181,9 @@ def solve_batched(lib, method, fun, jac, X0, lb, ub, ftol, xtol, gtol,
     Xjac = torch.empty((B, n), dtype=f64, device=dev) if method == "dogbox" \
         else None
     lin = torch.empty((B, LS), dtype=f64, device=dev)
-    count = torch.zeros(1, dtype=torch.int32, device=dev)
+    # count[2] = problems still running after the last round (written by the
+    # round kernel itself, blsq_round_batched `count`)
+    count = torch.zeros(4, dtype=torch.int32, device=dev)
     # TRF: worklist of the problems that leave the Gauss-Newton shortcut
     # (blsq_round_batched `work`); BLSQ_TRF_TWO_KERNELS=0 -> single kernel
     rwork = None
@@ -226,7 +228,7 @@ def solve_batched(lib, method, fun, jac, X0, lb, ub, ftol, xtol, gtol,
     rounds = 0
     launches = 0
 
-    def one_round(A, idx, idx32, first, nrun, off=0):
+    def one_round(A, idx, idx32, first, nrun, off=0, count_here=True):
         """Callbacks + linearise + round for the A compacted slots (or, in the
         streaming prologue, for the A problems starting at problem `off`)."""
         nonlocal m, launches
@@ -294,18 +296,12 @@ def solve_batched(lib, method, fun, jac, X0, lb, ub, ftol, xtol, gtol,
                  p_x0, p_lb, p_ub, bstride, sc_ptr,
                  float(ftol), float(xtol), float(gtol), max_nfev, first,
                  p_st, p_ist, p_xn, p_xj,
-                 rwork_ptr if A >= TWO_KERNELS_ABOVE else None, stream)
+                 rwork_ptr if A >= TWO_KERNELS_ABOVE else None,
+                 count.data_ptr() if count_here else None, stream)
         tock("round", t0, nrun)
         if timers is not None:
             timers["shape"] = (n, m, LS, S)
         launches += 2 if (rwork is None or A < TWO_KERNELS_ABOVE) else 3
-
-    def count_running(A, idx32):
-        nonlocal launches
-        lib.call("blsq_count_running", A,
-                 None if idx32 is None else idx32.data_ptr(),
-                 istate.data_ptr(), count.data_ptr(), lib.stream(X0))
-        launches += 1
 
     def graph_tail(A, idx, idx32, nrun):
         """The latency-sized tail of the batch (A <= tail_below slots, often a
@@ -347,7 +343,6 @@ def solve_batched(lib, method, fun, jac, X0, lb, ub, ftol, xtol, gtol,
                 try:
                     for _ in range(GRAPH_ROUNDS):
                         one_round(A, idx, idx32, 0, nrun)
-                    count_running(A, idx32)
                 finally:
                     if dbg:
                         tt.append(time.perf_counter())
@@ -378,7 +373,7 @@ def solve_batched(lib, method, fun, jac, X0, lb, ub, ftol, xtol, gtol,
             g.replay()
             launches += per_replay
             r += GRAPH_ROUNDS
-            if int(count.item()) == 0 or rounds + r > max_nfev + 1:
+            if int(count[2].item()) == 0 or rounds + r > max_nfev + 1:
                 if dbg:
                     tt.append(time.perf_counter())
                     print("# graph tail A=%d: begin %.2f capture %.2f end %.2f "
@@ -402,7 +397,8 @@ def solve_batched(lib, method, fun, jac, X0, lb, ub, ftol, xtol, gtol,
             if ev is not None:
                 torch.cuda.current_stream(dev).wait_event(ev)
             for r in range(K):
-                one_round(c1 - c0, None, None, 1 if r == 0 else 0, c1 - c0, off=c0)
+                one_round(c1 - c0, None, None, 1 if r == 0 else 0, c1 - c0, off=c0,
+                          count_here=False)
         first = 0
         rounds = K
     while A > 0:
@@ -415,8 +411,7 @@ def solve_batched(lib, method, fun, jac, X0, lb, ub, ftol, xtol, gtol,
         # bandwidth-sized, every 4th once they are launch-latency sized
         every = check_every if A > tail_below else max(check_every, 4)
         if rounds % every == 0 or rounds >= max_nfev:
-            count_running(A, idx32)
-            nrun = int(count.item())                  # the one host sync
+            nrun = int(count[2].item())               # the one host sync
             if nrun == 0:
                 break
             if nrun <= compact_below * A:

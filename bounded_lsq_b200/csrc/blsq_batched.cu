@@ -309,7 +309,7 @@ lin_kernel(int64_t A, const int32_t* __restrict__ idx, int m,
 // that need the SVD route to work[1..] (work[0] = their number); MODE 2 then
 // finishes exactly those slots with dense warps (blsq_core.cuh trf_round_impl).
 template <int N, int METHOD, int MODE>
-__device__ __forceinline__ void
+__device__ __forceinline__ bool
 round_slot(int64_t slot, int64_t A, const int32_t* __restrict__ idx,
            const double* __restrict__ lin, const double* __restrict__ x0,
            const double* __restrict__ lb, const double* __restrict__ ub,
@@ -320,18 +320,38 @@ round_slot(int64_t slot, int64_t A, const int32_t* __restrict__ idx,
     typedef LinRec<N> L;
     constexpr int SS = (METHOD == BLSQ_METHOD_TRF) ? TrfState<N>::SIZE
                                                    : DogState<N>::SIZE;
-    constexpr int XNEW = N;
-    if (slot >= A) return;
+    if (slot >= A) return false;
     const int64_t pid = idx ? idx[slot] : slot;
-    int ist[IS_SIZE];
     int32_t* ip = istate + pid * IS_SIZE;
+    double sc[N];
+#pragma unroll
+    for (int i = 0; i < N; i++) sc[i] = scaling ? scaling[i] : 1.0;
+    if (METHOD == BLSQ_METHOD_TRF) {
+        // the records stay in memory: trf_round_impl fetches the blocks it
+        // needs when it needs them (256-bit loads) and stores what changed
+        int ist[4];
+        {
+            int4 t0 = *reinterpret_cast<const int4*>(ip);
+            ist[0] = t0.x; ist[1] = t0.y; ist[2] = t0.z; ist[3] = t0.w;
+        }
+        if (ist[IS_STATUS] != ST_RUNNING) return false;
+        const int rc = trf_round_impl<N, MODE>(
+            state + pid * (int64_t)SS, ist, lin + slot * (int64_t)L::SIZE, x0 + pid * N,
+            lb + pid * bstride, ub + pid * bstride, sc, P, first, Xnew + slot * N);
+        *reinterpret_cast<int4*>(ip) = make_int4(ist[0], ist[1], ist[2], ist[3]);
+        if (MODE == 1 && rc == TRF_DEFER)
+            work[1 + atomicAdd(work, 1)] = (int32_t)slot;
+        return ist[IS_STATUS] == ST_RUNNING;
+    }
+    constexpr int XNEW = N;
+    int ist[IS_SIZE];
     {
         int4 t0 = *reinterpret_cast<const int4*>(ip);
         int4 t1 = *reinterpret_cast<const int4*>(ip + 4);
         ist[0] = t0.x; ist[1] = t0.y; ist[2] = t0.z; ist[3] = t0.w;
         ist[4] = t1.x; ist[5] = t1.y; ist[6] = t1.z; ist[7] = t1.w;
     }
-    if (ist[IS_STATUS] != ST_RUNNING) return;
+    if (ist[IS_STATUS] != ST_RUNNING) return false;
     double st[SS];
     double* sp = state + pid * (int64_t)SS;
     if (SS % 2 == 0) {
@@ -346,7 +366,7 @@ round_slot(int64_t slot, int64_t A, const int32_t* __restrict__ idx,
         for (int i = 0; i < SS; i++) st[i] = sp[i];
     }
     double ln[L::SIZE];
-    if (MODE != 2) {             // the resumed part never reads the record
+    {
         const double* lp = lin + slot * (int64_t)L::SIZE;
 #pragma unroll
         for (int i = 0; i < L::SIZE; i += 2) {
@@ -355,20 +375,8 @@ round_slot(int64_t slot, int64_t A, const int32_t* __restrict__ idx,
             ln[i + 1] = t.y;
         }
     }
-    double sc[N];
-#pragma unroll
-    for (int i = 0; i < N; i++) sc[i] = scaling ? scaling[i] : 1.0;
-    bool go;
-    if (METHOD == BLSQ_METHOD_TRF) {
-        const int rc = trf_round_impl<N, MODE>(st, ist, ln, x0 + pid * N, lb + pid * bstride,
-                                               ub + pid * bstride, sc, P, first);
-        go = rc == 1;
-        if (MODE == 1 && rc == TRF_DEFER)
-            work[1 + atomicAdd(work, 1)] = (int32_t)slot;
-    } else {
-        go = dogbox_round<N>(st, ist, ln, x0 + pid * N, lb + pid * bstride,
-                             ub + pid * bstride, sc, P, first);
-    }
+    const bool go = dogbox_round<N>(st, ist, ln, x0 + pid * N, lb + pid * bstride,
+                                    ub + pid * bstride, sc, P, first);
     if (SS % 2 == 0) {
 #pragma unroll
         for (int i = 0; i < SS; i += 2)
@@ -386,17 +394,16 @@ round_slot(int64_t slot, int64_t A, const int32_t* __restrict__ idx,
 #pragma unroll
             for (int i = 0; i < N; i++) {
                 double xj = st[XNEW + i];
-                if (METHOD == BLSQ_METHOD_DOGBOX) {
-                    // the point dogbox.py:256-261 would evaluate J at
-                    int ob = ((ist[IS_FREE] >> i) & 1) ? get2(ist[IS_MARKS], i)
-                                                       : get2(ist[IS_ONB], i);
-                    if (ob == -1) xj = lb[pid * bstride + i];
-                    if (ob == 1) xj = ub[pid * bstride + i];
-                }
+                // the point dogbox.py:256-261 would evaluate J at
+                int ob = ((ist[IS_FREE] >> i) & 1) ? get2(ist[IS_MARKS], i)
+                                                   : get2(ist[IS_ONB], i);
+                if (ob == -1) xj = lb[pid * bstride + i];
+                if (ob == 1) xj = ub[pid * bstride + i];
                 Xjac[slot * N + i] = xj;
             }
         }
     }
+    return ist[IS_STATUS] == ST_RUNNING;
 }
 
 template <int N, int METHOD, int MODE>
@@ -407,7 +414,8 @@ round_kernel(int64_t A, const int32_t* __restrict__ idx,
              int bstride, const double* __restrict__ scaling, SolveParams P,
              int first, double* __restrict__ state,
              int32_t* __restrict__ istate, double* __restrict__ Xnew,
-             double* __restrict__ Xjac, int32_t* __restrict__ work) {
+             double* __restrict__ Xjac, int32_t* __restrict__ work,
+             int32_t* __restrict__ count) {
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (MODE == 2) {
         // the worklist length is only known on the device: a small grid
@@ -416,13 +424,33 @@ round_kernel(int64_t A, const int32_t* __restrict__ idx,
         for (int64_t w = tid; w < cnt; w += (int64_t)gridDim.x * blockDim.x)
             round_slot<N, METHOD, MODE>(work[1 + w], A, idx, lin, x0, lb, ub, bstride, scaling,
                                         P, first, state, istate, Xnew, Xjac, work);
-    } else {
-        round_slot<N, METHOD, MODE>(tid, A, idx, lin, x0, lb, ub, bstride, scaling, P, first,
-                                    state, istate, Xnew, Xjac, work);
+        return;
+    }
+    const bool run = round_slot<N, METHOD, MODE>(tid, A, idx, lin, x0, lb, ub, bstride, scaling,
+                                                 P, first, state, istate, Xnew, Xjac, work);
+    if (!count) return;
+    // running problems after this round: one atomic per CTA; the last CTA to
+    // arrive publishes the total in count[2] and re-arms the two counters, so
+    // the host needs no memset and no separate counting launch per round
+    __shared__ int block_run;
+    if (threadIdx.x == 0) block_run = 0;
+    __syncthreads();
+    const unsigned bal = __ballot_sync(0xffffffffu, run);
+    if ((threadIdx.x & 31) == 0 && bal) atomicAdd(&block_run, __popc(bal));
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (block_run) atomicAdd(count, block_run);
+        __threadfence();
+        const int ticket = atomicAdd(count + 1, 1);
+        if (ticket == (int)gridDim.x - 1) {
+            __threadfence();
+            count[2] = atomicExch(count, 0);
+            count[1] = 0;
+        }
     }
 }
 
-__global__ void init_kernel(int method, int64_t B, int n, int SS,
+__global__ void init_kernel(int method, int64_t B, int n, int SS, int XNEW,
                             const double* __restrict__ x0,
                             const double* __restrict__ lb,
                             const double* __restrict__ ub, int bstride,
@@ -436,7 +464,7 @@ __global__ void init_kernel(int method, int64_t B, int n, int SS,
     double x = x0[t];
     if (method == BLSQ_METHOD_TRF)
         x = strictly_feasible(x, lb[b * bstride + i], ub[b * bstride + i], 1e-10);
-    state[b * SS + n + i] = x;          // XNEW
+    state[b * SS + XNEW + i] = x;
     state[b * SS + i] = x;              // X
     Xnew[t] = x;
     if (i == 0) {
@@ -619,7 +647,7 @@ int launch_round(int method, int64_t A, const int32_t* idx, const double* lin,
                  const double* x0, const double* lb, const double* ub,
                  int bstride, const double* scaling, SolveParams P, int first,
                  double* state, int32_t* istate, double* Xnew, double* Xjac,
-                 int32_t* work, cudaStream_t s) {
+                 int32_t* work, int32_t* count, cudaStream_t s) {
     int64_t blocks = (A + BLSQ_ROUND_THREADS - 1) / BLSQ_ROUND_THREADS;
     if (blocks > 0x7fffffff) return BLSQ_E_UNSUPPORTED;
     const unsigned gb = (unsigned)blocks;
@@ -627,19 +655,23 @@ int launch_round(int method, int64_t A, const int32_t* idx, const double* lin,
         cudaError_t e = cudaMemsetAsync(work, 0, sizeof(int32_t), s);
         if (e != cudaSuccess) return (int)e;
         round_kernel<N, BLSQ_METHOD_TRF, 1><<<gb, BLSQ_ROUND_THREADS, 0, s>>>(
-            A, idx, lin, x0, lb, ub, bstride, scaling, P, first, state, istate, Xnew, Xjac, work);
+            A, idx, lin, x0, lb, ub, bstride, scaling, P, first, state, istate, Xnew, Xjac, work,
+            count);
         BLSQ_LAUNCH_CHECK();
         // ~5 % of the problems land on the worklist: an eighth of the grid
         // (at least 4 CTAs per SM) strides over it
         unsigned g2 = gb / 8 > 592u ? gb / 8 : (gb < 592u ? gb : 592u);
         round_kernel<N, BLSQ_METHOD_TRF, 2><<<g2, BLSQ_ROUND_THREADS, 0, s>>>(
-            A, idx, lin, x0, lb, ub, bstride, scaling, P, first, state, istate, Xnew, Xjac, work);
+            A, idx, lin, x0, lb, ub, bstride, scaling, P, first, state, istate, Xnew, Xjac, work,
+            nullptr);
     } else if (method == BLSQ_METHOD_TRF) {
         round_kernel<N, BLSQ_METHOD_TRF, 0><<<gb, BLSQ_ROUND_THREADS, 0, s>>>(
-            A, idx, lin, x0, lb, ub, bstride, scaling, P, first, state, istate, Xnew, Xjac, work);
+            A, idx, lin, x0, lb, ub, bstride, scaling, P, first, state, istate, Xnew, Xjac, work,
+            count);
     } else {
         round_kernel<N, BLSQ_METHOD_DOGBOX, 0><<<gb, BLSQ_ROUND_THREADS, 0, s>>>(
-            A, idx, lin, x0, lb, ub, bstride, scaling, P, first, state, istate, Xnew, Xjac, work);
+            A, idx, lin, x0, lb, ub, bstride, scaling, P, first, state, istate, Xnew, Xjac, work,
+            count);
     }
     BLSQ_LAUNCH_CHECK();
     return 0;
@@ -707,7 +739,7 @@ int blsq_init_batched(int method, int64_t B, int n, const double* x0,
     if (B == 0) return 0;
     int64_t blocks = (B * n + 255) / 256;
     init_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
-        method, B, n, lay[0], x0, lb, ub, bstride, state, istate, Xnew);
+        method, B, n, lay[0], lay[2], x0, lb, ub, bstride, state, istate, Xnew);
     BLSQ_LAUNCH_CHECK();
     return 0;
 }
@@ -737,18 +769,24 @@ int blsq_round_batched(int method, int64_t A, const int32_t* idx, int m, int n,
                        const double* ub, int bstride, const double* scaling,
                        double ftol, double xtol, double gtol, int max_nfev,
                        int first, double* state, int32_t* istate, double* Xnew,
-                       double* Xjac, int32_t* work, void* stream) {
+                       double* Xjac, int32_t* work, int32_t* count, void* stream) {
     if (A < 0 || !lin || !x0 || !lb || !ub || !state || !istate || !Xnew) return BLSQ_E_BADARG;
     if (method != BLSQ_METHOD_TRF && method != BLSQ_METHOD_DOGBOX) return BLSQ_E_BADARG;
     if (bstride != 0 && bstride != n) return BLSQ_E_BADARG;
-    if (A == 0) return 0;
+    if (A == 0) {
+        if (count) {
+            cudaError_t e = cudaMemsetAsync(count, 0, 3 * sizeof(int32_t), (cudaStream_t)stream);
+            if (e != cudaSuccess) return (int)e;
+        }
+        return 0;
+    }
     SolveParams P;
     P.ftol = ftol; P.xtol = xtol; P.gtol = gtol;
     P.max_nfev = max_nfev; P.m = m; P.jac_scaling = scaling ? 0 : 1;
     BLSQ_DISPATCH_N(n, {
         return launch_round<N_>(method, A, idx, lin, x0, lb, ub, bstride,
                                 scaling, P, first, state, istate, Xnew, Xjac,
-                                work, (cudaStream_t)stream);
+                                work, count, (cudaStream_t)stream);
     });
     return 0;
 }

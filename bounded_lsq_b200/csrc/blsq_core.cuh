@@ -539,28 +539,11 @@ BLSQ_HD double evaluate_quadratic(const double* Rh, const double* diag,
 // propose; see DESIGN.md "Batched rounds")
 // ---------------------------------------------------------------------------
 
-template <int N>
-struct TrfState {
-    // layout of one problem's record in the state array (doubles)
-    static constexpr int NT = N * (N + 1) / 2;
-    static constexpr int X = 0;            // accepted point
-    static constexpr int XNEW = N;         // trial point in flight
-    static constexpr int SCALE = 2 * N;    // 1/scaling, or running 'jac' scale
-    static constexpr int R = 3 * N;        // packed triangle of J = QR at X
-    static constexpr int QTF = R + NT;
-    static constexpr int G = QTF + N;      // J^T f at X
-    static constexpr int OBJ = G + N;      // f.f at X
-    static constexpr int DELTA = OBJ + 1;
-    static constexpr int ALPHA = OBJ + 2;
-    static constexpr int PRED = OBJ + 3;   // predicted reduction of the trial
-    static constexpr int CORR = OBJ + 4;   // step_h.diag_h.step_h
-    static constexpr int NSTEPH = OBJ + 5; // |step_h|
-    static constexpr int NSTEP = OBJ + 6;  // |step|
-    static constexpr int GNORM = OBJ + 7;  // optimality at the last linearise
-    static constexpr int SIZE = OBJ + 8;
-};
-
-// record produced by the linearise kernel for the trial point
+// Records are laid out in blocks that start at multiples of 4 doubles (32
+// bytes): every block moves with 256-bit loads / stores (LDG.E.256 on sm_100a,
+// a whole DRAM sector per instruction) and can be fetched on its own when the
+// round needs it, instead of the whole record sitting in registers.
+// LinRec: the record produced by the linearise kernel for the trial point.
 template <int N>
 struct LinRec {
     static constexpr int NT = N * (N + 1) / 2;
@@ -568,7 +551,30 @@ struct LinRec {
     static constexpr int QTF = NT;
     static constexpr int G = NT + N;
     static constexpr int OBJ = NT + 2 * N;
-    static constexpr int SIZE = ((NT + 2 * N + 1) + 1) & ~1;   // even
+    static constexpr int SIZE = (NT + 2 * N + 1 + 3) & ~3;     // multiple of 4
+};
+
+template <int N>
+struct TrfState {
+    // layout of one problem's record in the state array (doubles)
+    static constexpr int NT = N * (N + 1) / 2;
+    static constexpr int NP = (N + 3) & ~3;
+    static constexpr int X = 0;            // accepted point
+    static constexpr int XNEW = NP;        // trial point in flight
+    static constexpr int SCALE = 2 * NP;   // 1/scaling, or running 'jac' scale
+    static constexpr int R = 3 * NP;       // linearisation at X: same layout as LinRec
+    static constexpr int QTF = R + NT;
+    static constexpr int G = QTF + N;      // J^T f at X
+    static constexpr int OBJ = G + N;      // f.f at X
+    static constexpr int SCAL = R + LinRec<N>::SIZE;   // scalar block (8 doubles)
+    static constexpr int DELTA = SCAL;
+    static constexpr int ALPHA = SCAL + 1;
+    static constexpr int PRED = SCAL + 2;   // predicted reduction of the trial
+    static constexpr int CORR = SCAL + 3;   // step_h.diag_h.step_h
+    static constexpr int NSTEPH = SCAL + 4; // |step_h|
+    static constexpr int NSTEP = SCAL + 5;  // |step|
+    static constexpr int GNORM = SCAL + 6;  // optimality at the last linearise
+    static constexpr int SIZE = SCAL + 8;
 };
 
 struct SolveParams {
@@ -596,43 +602,230 @@ enum { IS_STATUS = 0, IS_NFEV = 1, IS_NJEV = 2, IS_ONB = 3, IS_MARKS = 4,
 // trial in st[XNEW]) or TRF_DEFER.
 enum { TRF_DEFER = 2 };
 
+// ---- block moves: 256-bit on the device when K % 4 == 0 (p 32-byte aligned) ----
+template <int K>
+BLSQ_HD void ld_block(const double* p, double* d) {
+#if defined(__CUDA_ARCH__)
+    if (K % 4 == 0) {
+        BLSQ_UNROLL
+        for (int i = 0; i < K; i += 4)
+            asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];"
+                         : "=d"(d[i]), "=d"(d[i + 1]), "=d"(d[i + 2]), "=d"(d[i + 3])
+                         : "l"(p + i));
+        return;
+    }
+#endif
+    BLSQ_UNROLL
+    for (int i = 0; i < K; i++) d[i] = p[i];
+}
+template <int K>
+BLSQ_HD void st_block(double* p, const double* v) {
+#if defined(__CUDA_ARCH__)
+    if (K % 4 == 0) {
+        BLSQ_UNROLL
+        for (int i = 0; i < K; i += 4)
+            asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p + i), "d"(v[i]),
+                         "d"(v[i + 1]), "d"(v[i + 2]), "d"(v[i + 3])
+                         : "memory");
+        return;
+    }
+#endif
+    BLSQ_UNROLL
+    for (int i = 0; i < K; i++) p[i] = v[i];
+}
+
+// Packed-triangle versions of hat_fold / gn_shortcut (same arithmetic as the
+// N x N forms above up to the Givens coefficients, which come from one
+// reciprocal square root instead of a square root and two divisions).
+// A: packed upper triangle (tri_index), in: R * diag(d); out: the triangle of
+// the QR factor of [R diag(d); diag(sqrt(diag_h))].  b: in Q^T f, out: rotated.
+template <int N>
+BLSQ_HD void hat_fold_packed(double* A, double* b, const double* diag_h) {
+    BLSQ_UNROLL
+    for (int k = 0; k < N; k++) {
+        double e = sqrt(diag_h[k]);
+        if (e == 0.0) continue;
+        double row[N];
+        BLSQ_UNROLL
+        for (int j = 0; j < N; j++) row[j] = (j == k) ? e : 0.0;
+        double bz = 0.0;
+        BLSQ_UNROLL
+        for (int i = 0; i < N; i++) {
+            if (i < k) continue;
+            double x = row[i];
+            if (x == 0.0) continue;
+            double a = A[tri_index<N>(i, i)];
+            double rinv = rsqrt_d(fma(a, a, x * x));
+            double c = a * rinv, sn = x * rinv;
+            BLSQ_UNROLL
+            for (int j = 0; j < N; j++) {
+                if (j < i) continue;
+                double aj = A[tri_index<N>(i, j)], rj = row[j];
+                A[tri_index<N>(i, j)] = fma(c, aj, sn * rj);
+                row[j] = fma(-sn, aj, c * rj);
+            }
+            double bi = b[i];
+            b[i] = fma(c, bi, sn * bz);
+            bz = fma(-sn, bi, c * bz);
+        }
+    }
+}
+
+template <int N>
+BLSQ_HD bool gn_shortcut_packed(const double* A, const double* b, int m, double Delta,
+                                double* p_h) {
+    if (m < N) return false;
+    double T[Tri<N>::size];
+    double fa = 0.0, ft = 0.0;
+    BLSQ_UNROLL
+    for (int i = 0; i < N; i++) {
+        const double aii = A[tri_index<N>(i, i)];
+        if (!(aii != 0.0)) return false;
+        T[tri_index<N>(i, i)] = 1.0 / aii;
+    }
+    BLSQ_UNROLL
+    for (int i = 0; i < N; i++) {
+        BLSQ_UNROLL
+        for (int j = 0; j < N; j++) {
+            if (j < i) continue;
+            const double aij = A[tri_index<N>(i, j)];
+            fa = fma(aij, aij, fa);
+            if (j > i) {
+                double acc = 0.0;
+                BLSQ_UNROLL
+                for (int k = 0; k < N; k++) {
+                    if (k < i || k >= j) continue;
+                    acc = fma(T[tri_index<N>(i, k)], A[tri_index<N>(k, j)], acc);
+                }
+                T[tri_index<N>(i, j)] = -acc * T[tri_index<N>(j, j)];
+            }
+            ft = fma(T[tri_index<N>(i, j)], T[tri_index<N>(i, j)], ft);
+        }
+    }
+    const double em = EPS * m;
+    if (!(fa * ft * (em * em) < 0.0625)) return false;     // also rejects NaN / inf
+    double nn = 0.0;
+    BLSQ_UNROLL
+    for (int ii = 0; ii < N; ii++) {
+        const int i = N - 1 - ii;
+        double num = -b[i];
+        BLSQ_UNROLL
+        for (int j = 0; j < N; j++) {
+            if (j <= i) continue;
+            num = fma(-A[tri_index<N>(i, j)], p_h[j], num);
+        }
+        const double r = T[tri_index<N>(i, i)];
+        double q = num * r;
+        q = fma(fma(-q, A[tri_index<N>(i, i)], num), r, q);   // correctly rounded quotient
+        p_h[i] = q;
+        nn = fma(q, q, nn);
+    }
+    return sqrt(nn) <= Delta * (1.0 - 1e-9);
+}
+
+// y = R (d o s) for the packed triangle R: J_h s in the rotated frame
+template <int N>
+BLSQ_HD void tri_matvec_d(const double* R, const double* d, const double* s, double* y) {
+    BLSQ_UNROLL
+    for (int i = 0; i < N; i++) {
+        double acc = 0.0;
+        BLSQ_UNROLL
+        for (int j = i; j < N; j++) {
+            // R[i][j] * d[j] is the entry of R diag(d) (J_h in the rotated frame)
+            acc = fma(R[tri_index<N>(i, j)] * d[j], s[j], acc);
+        }
+        y[i] = acc;
+    }
+}
+
+template <int N>
+BLSQ_HD double evaluate_quadratic_d(const double* R, const double* d, const double* diag,
+                                    const double* g, const double* s) {
+    double v[N];
+    tri_matvec_d<N>(R, d, s, v);
+    double sd = 0.0;
+    BLSQ_UNROLL
+    for (int i = 0; i < N; i++) sd = fma(diag[i], s[i] * s[i], sd);
+    return 0.5 * (dot<N>(v, v) + sd) + dot<N>(s, g);
+}
+
+template <int N>
+BLSQ_HD void build_quadratic_1d_d(const double* R, const double* d, const double* diag,
+                                  const double* g, const double* s, const double* s0,
+                                  double& a, double& b) {
+    double v[N];
+    tri_matvec_d<N>(R, d, s, v);
+    double sd = 0.0;
+    BLSQ_UNROLL
+    for (int i = 0; i < N; i++) sd = fma(s[i] * diag[i], s[i], sd);
+    a = 0.5 * (dot<N>(v, v) + sd);
+    b = dot<N>(g, s);
+    if (s0) {
+        double u[N];
+        tri_matvec_d<N>(R, d, s0, u);
+        double s0d = 0.0;
+        BLSQ_UNROLL
+        for (int i = 0; i < N; i++) s0d = fma(s0[i] * diag[i], s[i], s0d);
+        b += dot<N>(u, v) + s0d;
+    }
+}
+
+// One TRF round for one problem, working on the records IN MEMORY: `sp` the
+// state record (TrfState layout), `lp` the linearisation record of the trial
+// point (LinRec), both 32-byte aligned.  Blocks are loaded when the round gets
+// to them and stored when they change, so the live register set stays small
+// (the first version held all 39 + 20 doubles of an N = 4 problem in
+// registers from the first to the last instruction: 128 registers plus 528-860
+// bytes of spills, profiles/r1_c2_round_kernel_ncu.md).  ist: the first four
+// istate words in registers (status, nfev, njev, -).
 template <int N, int MODE>
-BLSQ_HD int trf_round_impl(double* st, int* ist, const double* lin,
+BLSQ_HD int trf_round_impl(double* sp, int* ist, const double* lp,
                            const double* x0, const double* lb, const double* ub,
-                           const double* scaling, const SolveParams& P, int first) {
+                           const double* scaling, const SolveParams& P, int first,
+                           double* xout = nullptr) {
     typedef TrfState<N> S;
     typedef LinRec<N> L;
+    constexpr int NP = S::NP;
     int status = ST_RUNNING;     // pending status set by the inner loop
     bool adopt = false;
+    double sc[8];                // DELTA ALPHA PRED CORR NSTEPH NSTEP GNORM -
+    ld_block<8>(sp + S::SCAL, sc);
+    double blk[L::SIZE];         // R, QTF, G, OBJ of the point the round works at
+    double x[NP];
     if (MODE == 2) {
         first = 0;               // scale / Delta / alpha are in the state already
+        ld_block<NP>(sp + S::X, x);
+        ld_block<L::SIZE>(sp + S::R, blk);
     } else if (first) {
         // trf.py:201-235
         ist[IS_NFEV] = 1;
         ist[IS_NJEV] = 0;
         adopt = true;
-        st[S::ALPHA] = 0.0;
+        sc[1] = 0.0;             // alpha
+        ld_block<L::SIZE>(lp, blk);
     } else {
         // judge the trial (trf.py:310-344)
+        ld_block<L::SIZE>(lp, blk);
+        ld_block<NP>(sp + S::X, x);
         int nfev = ++ist[IS_NFEV];
-        double obj = st[S::OBJ];
-        double obj_new = lin[L::OBJ];
+        double obj = sp[S::OBJ];
+        double obj_new = blk[L::OBJ];
         double actual = obj - obj_new;
-        double pred = st[S::PRED];
-        double ratio = (pred > 0) ? (actual - st[S::CORR]) / pred : 0.0;
-        double nsh = st[S::NSTEPH];
-        double Delta = st[S::DELTA];
+        double pred = sc[2];
+        double ratio = (pred > 0) ? (actual - sc[3]) / pred : 0.0;
+        double nsh = sc[4];
+        double Delta = sc[0];
         if (ratio < 0.25) {
             double Dn = 0.25 * nsh;
-            st[S::ALPHA] *= Delta / Dn;
-            st[S::DELTA] = Dn;
+            sc[1] *= Delta / Dn;
+            sc[0] = Dn;
         } else if (ratio > 0.75 && nsh > 0.95 * Delta) {
-            st[S::DELTA] = Delta * 2.0;
-            st[S::ALPHA] *= 0.5;
+            sc[0] = Delta * 2.0;
+            sc[1] *= 0.5;
         }
         bool f_ok = fabs(actual) < P.ftol * obj && ratio > 0.25;
-        double xn = norm2<N>(st + S::X);
-        bool x_ok = st[S::NSTEP] < P.xtol * (SQRT_EPS > xn ? SQRT_EPS : xn);
+        double xn = norm2<N>(x);
+        bool x_ok = sc[5] < P.xtol * (SQRT_EPS > xn ? SQRT_EPS : xn);
         if (f_ok && x_ok) status = 4;
         else if (f_ok) status = 2;
         else if (x_ok) status = 3;
@@ -642,49 +835,49 @@ BLSQ_HD int trf_round_impl(double* st, int* ist, const double* lin,
             // inner loop decided; an accepted last step is still taken and
             // its Jacobian counted (trf.py:346-352)
             if (adopt) {
-                BLSQ_UNROLL
-                for (int i = 0; i < N; i++) st[S::X + i] = st[S::XNEW + i];
-                BLSQ_UNROLL
-                for (int i = 0; i < L::OBJ + 1; i++) st[S::R + i] = lin[i];
+                ld_block<NP>(sp + S::XNEW, x);
+                st_block<NP>(sp + S::X, x);
+                st_block<L::SIZE>(sp + S::R, blk);
                 ist[IS_NJEV]++;
             }
+            st_block<8>(sp + S::SCAL, sc);
             ist[IS_STATUS] = 0;
-            return false;
+            return 0;
         }
     }
     if (adopt) {
-        BLSQ_UNROLL
-        for (int i = 0; i < N; i++) st[S::X + i] = st[S::XNEW + i];
-        // R, QTF, G, OBJ are contiguous in both records
-        BLSQ_UNROLL
-        for (int i = 0; i < L::OBJ + 1; i++) st[S::R + i] = lin[i];
+        // the trial becomes the point; R, QTF, G, OBJ are contiguous and in the
+        // same order in both records
+        ld_block<NP>(sp + S::XNEW, x);
+        st_block<NP>(sp + S::X, x);
+        st_block<L::SIZE>(sp + S::R, blk);
         ist[IS_NJEV]++;
+    } else if (MODE != 2) {
+        ld_block<L::SIZE>(sp + S::R, blk);        // rejected: back to the old factor
     }
     if (first && 1 >= P.max_nfev) {          // `while nfev < max_nfev` never entered
-        st[S::GNORM] = dnan();
+        sc[6] = dnan();
+        st_block<8>(sp + S::SCAL, sc);
         ist[IS_STATUS] = 0;
-        return false;
+        return 0;
     }
 
-    // ---- linearise (trf.py:239-277) at st[X] ----
-    double x[N], g[N], scale[N], v[N], jv[N], d[N], g_h[N], diag_h[N];
+    // ---- linearise (trf.py:239-277) at x ----
+    const double* Rm = blk + L::R;
+    double scale[NP], d[N], g_h[N], diag_h[N], v[N];
     double l[N], u[N];
     BLSQ_UNROLL
-    for (int i = 0; i < N; i++) {
-        x[i] = st[S::X + i];
-        g[i] = st[S::G + i];
-        l[i] = lb[i];
-        u[i] = ub[i];
-    }
+    for (int i = 0; i < N; i++) { l[i] = lb[i]; u[i] = ub[i]; }
     if (P.jac_scaling) {
         // trf.py:216-221 (first) / 239-242 (running minimum); the column
         // norms of J are those of its triangular factor
+        if (!first) ld_block<NP>(sp + S::SCALE, scale);
         BLSQ_UNROLL
         for (int j = 0; j < N; j++) {
             double nn = 0.0;
             BLSQ_UNROLL
             for (int i = 0; i <= j; i++) {
-                double r = st[S::R + tri_index<N>(i, j)];
+                double r = Rm[tri_index<N>(i, j)];
                 nn = fma(r, r, nn);
             }
             double cn = sqrt(nn);
@@ -692,28 +885,29 @@ BLSQ_HD int trf_round_impl(double* st, int* ist, const double* lin,
                 if (cn == 0) cn = 1.0;
                 scale[j] = 1.0 / cn;
             } else {
-                scale[j] = np_min(st[S::SCALE + j], 1.0 / cn);
+                scale[j] = np_min(scale[j], 1.0 / cn);
             }
-            st[S::SCALE + j] = scale[j];
         }
+        BLSQ_UNROLL
+        for (int j = N; j < NP; j++) scale[j] = 0.0;
+        if (MODE != 2) st_block<NP>(sp + S::SCALE, scale);
     } else if (first) {
         BLSQ_UNROLL
-        for (int j = 0; j < N; j++) {
-            scale[j] = 1.0 / scaling[j];
-            st[S::SCALE + j] = scale[j];
-        }
+        for (int j = 0; j < NP; j++) scale[j] = (j < N) ? 1.0 / scaling[j] : 0.0;
+        st_block<NP>(sp + S::SCALE, scale);
     } else {
-        BLSQ_UNROLL
-        for (int j = 0; j < N; j++) scale[j] = st[S::SCALE + j];
+        ld_block<NP>(sp + S::SCALE, scale);
     }
     double g_norm = 0.0;
     BLSQ_UNROLL
     for (int i = 0; i < N; i++) {
-        cl_scaling(x[i], g[i], l[i], u[i], v[i], jv[i]);
+        double jv;
+        const double gi = blk[L::G + i];
+        cl_scaling(x[i], gi, l[i], u[i], v[i], jv);
         d[i] = sqrt(v[i]) * scale[i];
-        g_h[i] = d[i] * g[i];
-        diag_h[i] = g[i] * jv[i] * (scale[i] * scale[i]);
-        double gv = fabs(g[i] * v[i]);
+        g_h[i] = d[i] * gi;
+        diag_h[i] = gi * jv * (scale[i] * scale[i]);
+        double gv = fabs(gi * v[i]);
         if (gv > g_norm || gv != gv) g_norm = gv;
     }
     if (first) {
@@ -722,52 +916,64 @@ BLSQ_HD int trf_round_impl(double* st, int* ist, const double* lin,
         BLSQ_UNROLL
         for (int i = 0; i < N; i++) q[i] = x0[i] / (scale[i] * sqrt(v[i]));
         double D0 = norm2<N>(q);
-        st[S::DELTA] = (D0 == 0) ? 1.0 : D0;
+        sc[0] = (D0 == 0) ? 1.0 : D0;
     }
-    st[S::GNORM] = g_norm;
+    sc[6] = g_norm;
     if (g_norm < P.gtol) status = 1;              // trf.py:252-254 (overrides)
     if (status != ST_RUNNING) {
+        st_block<8>(sp + S::SCAL, sc);
         ist[IS_STATUS] = status;
-        return false;
+        return 0;
     }
 
-    double Rh[S::NT];
     double theta = 1.0 - g_norm;
     if (theta < 0.995) theta = 0.995;
 
     // ---- propose (trf.py:284-308) ----
-    double Delta = st[S::DELTA];
-    double alpha = st[S::ALPHA];
+    const double Delta = sc[0];
+    double alpha = sc[1];
     double p_h[N], p[N];
     {
-        double A[N * N], b[N];
-        hat_fold<N>(st + S::R, st + S::QTF, d, diag_h, Rh, A, b);
+        double A[S::NT], b[N];
+        BLSQ_UNROLL
+        for (int i = 0; i < N; i++) {
+            b[i] = blk[L::QTF + i];
+            BLSQ_UNROLL
+            for (int j = i; j < N; j++)
+                A[tri_index<N>(i, j)] = Rm[tri_index<N>(i, j)] * d[j];
+        }
+        hat_fold_packed<N>(A, b, diag_h);
         // every mode takes the same decision with the same arithmetic, so the
         // result does not depend on how the driver splits the work
-        if (MODE != 2 && gn_shortcut<N>(A, b, P.m, Delta, p_h)) {
+        if (MODE != 2 && gn_shortcut_packed<N>(A, b, P.m, Delta, p_h)) {
             alpha = 0.0;                           // trust_region.py:117
         } else if (MODE == 1) {
+            st_block<8>(sp + S::SCAL, sc);         // Delta / alpha of the judge, g_norm
             return TRF_DEFER;
         } else {
             // does the hat-space matrix have an exactly zero column?
             bool zero_col = false;
+            double Af[N * N];
             BLSQ_UNROLL
             for (int j = 0; j < N; j++) {
                 bool z = true;
                 BLSQ_UNROLL
-                for (int i = 0; i < N; i++)
-                    if (i <= j) z = z && (A[i * N + j] == 0.0);
+                for (int i = 0; i < N; i++) {
+                    Af[i * N + j] = (i <= j) ? A[tri_index<N>(i <= j ? i : j, j)] : 0.0;
+                    if (i <= j) z = z && (Af[i * N + j] == 0.0);
+                }
                 zero_col = zero_col || z;
             }
-            double s[N], Vt[N * N], suf[N];
-            hat_finish<N>(A, b, s, Vt, suf);
-            solve_lsq_trust_region<N>(P.m, suf, s, Vt, Delta, alpha, p_h, zero_col);
+            double sv[N], Vt[N * N], suf[N];
+            hat_finish<N>(Af, b, sv, Vt, suf);
+            solve_lsq_trust_region<N>(P.m, suf, sv, Vt, Delta, alpha, p_h, zero_col);
         }
     }
-    st[S::ALPHA] = alpha;
+    sc[1] = alpha;
     BLSQ_UNROLL
     for (int i = 0; i < N; i++) p[i] = d[i] * p_h[i];
-    double to_bound = step_size_to_bound<N>(x, p, l, u, nullptr);
+    int hits[N];
+    double to_bound = step_size_to_bound<N>(x, p, l, u, hits);
     double step_h[N];
     double qbest;
     if (to_bound >= 1) {
@@ -775,11 +981,10 @@ BLSQ_HD int trf_round_impl(double* st, int* ist, const double* lin,
         double f = tb < 1 ? tb : 1;
         BLSQ_UNROLL
         for (int i = 0; i < N; i++) step_h[i] = p_h[i] * f;
-        qbest = evaluate_quadratic<N>(Rh, diag_h, g_h, step_h);
+        qbest = evaluate_quadratic_d<N>(Rm, d, diag_h, g_h, step_h);
     } else {
-        // find_reflected_step, trf.py:105-156
-        int hits[N];
-        double stride_p = step_size_to_bound<N>(x, p, l, u, hits);
+        // find_reflected_step, trf.py:105-156 (the hits are those of to_bound)
+        double stride_p = to_bound;
         double r_h[N], r[N], x_edge[N];
         BLSQ_UNROLL
         for (int i = 0; i < N; i++) {
@@ -791,7 +996,11 @@ BLSQ_HD int trf_round_impl(double* st, int* ist, const double* lin,
         }
         double t_lo, to_tr;
         int err = intersect_trust_region<N>(p_h, r_h, Delta, t_lo, to_tr);
-        if (err) { ist[IS_STATUS] = err; return false; }
+        if (err) {
+            st_block<8>(sp + S::SCAL, sc);
+            ist[IS_STATUS] = err;
+            return 0;
+        }
         double tb2 = step_size_to_bound<N>(x_edge, r, l, u, nullptr);
         tb2 *= theta;
         double hi = tb2 < to_tr ? tb2 : to_tr;          // Python min(a, b)
@@ -800,7 +1009,7 @@ BLSQ_HD int trf_round_impl(double* st, int* ist, const double* lin,
         bool have_r = false;
         if (lo <= hi) {
             double a, b;
-            build_quadratic_1d<N>(Rh, diag_h, g_h, r_h, p_h, a, b);
+            build_quadratic_1d_d<N>(Rm, d, diag_h, g_h, r_h, p_h, a, b);
             double t = minimize_quadratic(a, b, lo, hi);
             BLSQ_UNROLL
             for (int i = 0; i < N; i++) refl[i] = p_h[i] + r_h[i] * t;
@@ -821,15 +1030,15 @@ BLSQ_HD int trf_round_impl(double* st, int* ist, const double* lin,
         double ttr = Delta / norm2<N>(g_h);
         double hig = tbg < ttr ? tbg : ttr;
         double ag, bg;
-        build_quadratic_1d<N>(Rh, diag_h, g_h, ng, nullptr, ag, bg);
+        build_quadratic_1d_d<N>(Rm, d, diag_h, g_h, ng, nullptr, ag, bg);
         double tg = minimize_quadratic(ag, bg, 0.0, hig);
         double c_h[N];
         BLSQ_UNROLL
         for (int i = 0; i < N; i++) c_h[i] = -tg * g_h[i];
         // trf.py:300-305: argmin, first minimum wins
-        double q0 = evaluate_quadratic<N>(Rh, diag_h, g_h, p_h);
-        double q1 = evaluate_quadratic<N>(Rh, diag_h, g_h, refl);
-        double q2 = evaluate_quadratic<N>(Rh, diag_h, g_h, c_h);
+        double q0 = evaluate_quadratic_d<N>(Rm, d, diag_h, g_h, p_h);
+        double q1 = evaluate_quadratic_d<N>(Rm, d, diag_h, g_h, refl);
+        double q2 = evaluate_quadratic_d<N>(Rm, d, diag_h, g_h, c_h);
         int k = 0;
         qbest = q0;
         if (q1 < qbest) { k = 1; qbest = q1; }
@@ -838,19 +1047,26 @@ BLSQ_HD int trf_round_impl(double* st, int* ist, const double* lin,
         for (int i = 0; i < N; i++)
             step_h[i] = (k == 0) ? p_h[i] : (k == 1 ? refl[i] : c_h[i]);
     }
-    double step[N];
-    double corr = 0.0;
+    double xn[NP];
+    double corr = 0.0, nsh2 = 0.0, ns2 = 0.0;
     BLSQ_UNROLL
     for (int i = 0; i < N; i++) {
-        step[i] = d[i] * step_h[i];
+        const double stp = d[i] * step_h[i];
         corr = fma(step_h[i] * diag_h[i], step_h[i], corr);
-        st[S::XNEW + i] = strictly_feasible(x[i] + step[i], l[i], u[i], 0.0);
+        nsh2 = fma(step_h[i], step_h[i], nsh2);
+        ns2 = fma(stp, stp, ns2);
+        xn[i] = strictly_feasible(x[i] + stp, l[i], u[i], 0.0);
     }
-    st[S::PRED] = -2 * qbest;
-    st[S::CORR] = corr;
-    st[S::NSTEPH] = norm2<N>(step_h);
-    st[S::NSTEP] = norm2<N>(step);
-    return true;
+    BLSQ_UNROLL
+    for (int i = N; i < NP; i++) xn[i] = 0.0;
+    st_block<NP>(sp + S::XNEW, xn);
+    if (xout) st_block<N>(xout, xn);       // the trial point handed to the callbacks
+    sc[2] = -2 * qbest;
+    sc[3] = corr;
+    sc[4] = sqrt(nsh2);
+    sc[5] = sqrt(ns2);
+    st_block<8>(sp + S::SCAL, sc);
+    return 1;
 }
 
 // One TRF round the way the two-kernel device path runs it: Gauss-Newton

@@ -150,13 +150,17 @@ int blsq_linearise_batched(int64_t A, const int32_t* idx, int m, int n,
  * every problem takes the Gauss-Newton shortcut of solve_lsq_trust_region
  * (trust_region.py:108-117: full rank certified, |p| <= Delta; ~95 % of the
  * solves) and the rest are collected in `work` and finished through the SVD
- * route with dense warps.  Without it (or for dogbox): one kernel. */
+ * route with dense warps.  Without it (or for dogbox): one kernel.
+ * count (nullable, 4 int32, zero before the first use): count[2] receives the
+ * number of slots still running after this round (what blsq_count_running
+ * would return) at no extra launch: one atomic per CTA into count[0], the
+ * last CTA to finish publishes the total and re-arms count[0..1]. */
 int blsq_round_batched(int method, int64_t A, const int32_t* idx, int m, int n,
                        const double* lin, const double* x0, const double* lb,
                        const double* ub, int bstride, const double* scaling,
                        double ftol, double xtol, double gtol, int max_nfev,
                        int first, double* state, int32_t* istate, double* Xnew,
-                       double* Xjac, int32_t* work, void* stream);
+                       double* Xjac, int32_t* work, int32_t* count, void* stream);
 
 /* dogbox.py:152-154,254: on_bound as the reference's int array (B x n) */
 int blsq_dogbox_on_bound(int64_t B, int n, const int32_t* istate,

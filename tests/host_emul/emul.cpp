@@ -241,7 +241,7 @@ int blsq_init_batched(int method, int64_t B, int n, const double* x0,
             double x = x0[b * n + i];
             if (method == BLSQ_METHOD_TRF)
                 x = strictly_feasible(x, lb[b * bs + i], ub[b * bs + i], 1e-10);
-            state[b * SS + n + i] = x;
+            state[b * SS + lay[2] + i] = x;
             state[b * SS + i] = x;
             Xnew[b * n + i] = x;
         }
@@ -271,7 +271,7 @@ int blsq_round_batched(int method, int64_t A, const int32_t* idx, int m, int n,
                        const double* ub, int bs, const double* scaling,
                        double ftol, double xtol, double gtol, int max_nfev,
                        int first, double* state, int32_t* istate, double* Xnew,
-                       double* Xjac, int32_t* /*work*/, void*) {
+                       double* Xjac, int32_t* /*work*/, int32_t* count, void*) {
     SolveParams P;
     P.ftol = ftol; P.xtol = xtol; P.gtol = gtol;
     P.max_nfev = max_nfev; P.m = m; P.jac_scaling = scaling ? 0 : 1;
@@ -285,7 +285,9 @@ int blsq_round_batched(int method, int64_t A, const int32_t* idx, int m, int n,
             const double* ln = lin + s * LinRec<N_>::SIZE;
             bool go;
             double* st;
+            int xnew_off = N_;
             if (method == BLSQ_METHOD_TRF) {
+                xnew_off = TrfState<N_>::XNEW;
                 st = state + pid * TrfState<N_>::SIZE;
                 go = trf_round<N_>(st, ist, ln, x0 + pid * N_, lb + pid * bs,
                                    ub + pid * bs, sc, P, first);
@@ -296,7 +298,7 @@ int blsq_round_batched(int method, int64_t A, const int32_t* idx, int m, int n,
             }
             if (go) {
                 for (int i = 0; i < N_; i++) {
-                    double xn = st[N_ + i];
+                    double xn = st[xnew_off + i];
                     Xnew[s * N_ + i] = xn;
                     if (Xjac) {
                         double xj = xn;
@@ -313,6 +315,12 @@ int blsq_round_batched(int method, int64_t A, const int32_t* idx, int m, int n,
             }
         }
     });
+    if (count) {
+        int c = 0;
+        for (int64_t s = 0; s < A; s++)
+            c += istate[(idx ? idx[s] : s) * IS_SIZE + IS_STATUS] == ST_RUNNING;
+        count[2] = c;
+    }
     return 0;
 }
 

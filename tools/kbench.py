@@ -68,12 +68,14 @@ def main():
                  None if J is None else J.data_ptr(), plist, dxp, mode,
                  istate.data_ptr(), lin.data_ptr(), st)
 
-    def t_round():
-        istate[:, 0] = -1
+    CNT = torch.zeros(4, dtype=torch.int32, device=dev)
+
+    def call_round(first):
         lib.call("blsq_round_batched", method, B, None, m, n, lin.data_ptr(),
                  X0.data_ptr(), lb.data_ptr(), ub.data_ptr(), 0, sc.data_ptr(),
-                 1.5e-8, 1.5e-8, 1.5e-8, 100 * n, 1, state.data_ptr(),
-                 istate.data_ptr(), Xnew.data_ptr(), None, RW, st)
+                 1.5e-8, 1.5e-8, 1.5e-8, 100 * n, first, state.data_ptr(),
+                 istate.data_ptr(), Xnew.data_ptr(),
+                 None if Xjac is None else Xjac.data_ptr(), RW, CNT.data_ptr(), st)
 
     def timeit(fn, pre=None):
         ts = []
@@ -90,19 +92,34 @@ def main():
                 ts.append(e0.elapsed_time(e1))
         return float(np.median(ts)), float(np.min(ts))
 
+    Xjac = torch.empty_like(Xnew) if a.workload != "c2" else None
     lin_ms, lin_min = timeit(t_lin)
-    istate[:, 0] = -1
+    # round 1 (first = 1), then the steady-state round: callbacks at the trial
+    # points, linearise, and the judge + propose round timed from a restored
+    # copy of the state
+    call_round(1)
+    Xj = Xnew if Xjac is None else Xjac
+    F = model.fun_t(Xnew, y).contiguous()
+    if a.workload == "c2":
+        J = model.jac_t(Xj, y).contiguous()
+    else:
+        lib.call("blsq_fd2_points", B, None, n, Xj.data_ptr(), lb.data_ptr(),
+                 ub.data_ptr(), 0, float("nan"), Xp.data_ptr(), dx.data_ptr(), st)
+        Fp = [model.fun_t(Xp[i], y).contiguous() for i in range(n)]
+        arr = (C.c_void_p * n)(*[t.data_ptr() for t in Fp])
+        plist = C.cast(arr, C.c_void_p)
+    t_lin()
+    state0, istate0 = state.clone(), istate.clone()
 
-    def round_only():
-        lib.call("blsq_round_batched", method, B, None, m, n, lin.data_ptr(),
-                 X0.data_ptr(), lb.data_ptr(), ub.data_ptr(), 0, sc.data_ptr(),
-                 1.5e-8, 1.5e-8, 1.5e-8, 100 * n, 1, state.data_ptr(),
-                 istate.data_ptr(), Xnew.data_ptr(), None, RW, st)
+    def restore():
+        state.copy_(state0)
+        istate.copy_(istate0)
 
-    def reset():
-        istate[:, 0].fill_(-1)
-
-    rnd_ms, rnd_min = timeit(round_only, reset)
+    rnd_ms, rnd_min = timeit(lambda: call_round(0), restore)
+    restore()
+    call_round(0)
+    torch.cuda.synchronize()
+    running = int(CNT[2].item())
     lin_bytes = B * (8 * m * (n + 1) + 8 * LS)
     rnd_bytes = B * (8 * LS + 16 * S + 64 + 8 * n)
     print(json.dumps(dict(
@@ -110,7 +127,7 @@ def main():
         lin_ms=lin_ms, lin_min_ms=lin_min, lin_gbs=lin_bytes / lin_ms / 1e6,
         lin_frac=lin_bytes / lin_ms / 1e6 / 6535.1,
         round_ms=rnd_ms, round_min_ms=rnd_min,
-        round_gbs=rnd_bytes / rnd_ms / 1e6)))
+        round_gbs=rnd_bytes / rnd_ms / 1e6, running_after=running)))
 
 
 if __name__ == "__main__":
