@@ -774,13 +774,18 @@ def run_batched(args, w, wname, steps, warmup, B, cpu_baseline=True):
         e1 = torch.cuda.Event(enable_timing=True)
         barrier()
         e0.record()
+        marks = [e0]
         for _ in range(steps):
             outs = solve(y_dev, x0_dev)
             launches += sum(o.kernel_launches for o in outs)
             rounds += sum(o.rounds for o in outs)
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            marks.append(ev)
         e1.record()
         barrier()
     dev_ms = reduce_max(e0.elapsed_time(e1))
+    per_step_ms = [a.elapsed_time(b) for a, b in zip(marks, marks[1:])]
     value = world * B * steps / (dev_ms * 1e-3)
     status = torch.cat([o.status for o in outs])
     nfev_mean = float(torch.cat([o.nfev for o in outs]).double().mean())
@@ -893,7 +898,8 @@ def run_batched(args, w, wname, steps, warmup, B, cpu_baseline=True):
             data_pool="%d distinct seeded problems per GPU tiled to %d "
                       "(same traffic; host generation time)" % (ngen, B),
             mean_nfev=nfev_mean, mean_njev=njev_mean, converged_frac=converged,
-            rounds_per_step=rounds / steps),
+            rounds_per_step=rounds / steps,
+            per_step_ms=[round(v, 3) for v in per_step_ms]),
         "e2e": {"value": e2e_value, "unit": "fits/s",
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms / steps},

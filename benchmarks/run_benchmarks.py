@@ -10,8 +10,9 @@ active, status) and the same row order as the reference's driver, restricted
 to the solvers that are on the hot path: ``dogbox``, ``dogbox-s``, ``trf``,
 ``trf-s`` for the unbounded problems and ``dogbox``, ``trf`` for the bounded
 ones (``lm``, ``leastsqbound`` and ``l-bfgs-b`` are MINPACK / L-BFGS-B
-wrappers, SURVEY 8f "out of scope").  The problems are the MGH/MINPACK-style
-instances of ``tests/problems.py``; every solve goes through
+wrappers, SURVEY 8f "out of scope").  The problems are the 32 unbounded + 26
+bounded instances of the reference suite (``extract_lsq_problems``,
+lsq_problems.py:1003-1018) restated in ``tests/problems.py``; every solve goes through
 ``bounded_lsq_b200.least_squares`` (heterogeneous (m, n): n <= 8 runs on the
 batched kernels with B = 1, larger even n on the tall-mode kernels).
 
@@ -104,7 +105,7 @@ def run_benchmark(lib, dev, problems, ftol, xtol, gtol, jac, methods, name,
     return rows
 
 
-def main(argv=None, lib=None, dev=None):
+def main(argv=None, lib=None, dev=None, max_n=None):
     tol = np.finfo(float).eps ** 0.5
     ap = argparse.ArgumentParser()
     ap.add_argument("output", nargs="?", type=str, help="Output file.")
@@ -119,7 +120,7 @@ def main(argv=None, lib=None, dev=None):
     out = open(args.output, "w") if args.output else sys.stdout
     lib = lib or get_lib()
     dev = dev or torch.device("cuda:0")
-    probs = corpus()
+    probs = corpus(max_n)
     unb = [p for p in probs if np.all(np.isinf(p.lb)) and np.all(np.isinf(p.ub))]
     bnd = [p for p in probs if p not in unb]
     if not args.u and not args.b:

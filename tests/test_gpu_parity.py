@@ -81,9 +81,10 @@ def test_per_problem_bounds(lib, dev):
 
 
 def test_corpus_single(lib, dev):
+    """Config #1: all 58 instances of the reference suite x 7 variants."""
     st = cases.check_corpus_single(lib, dev)
     print(st)
-    assert st["exact_status"] >= 60
+    assert st["total"] == 406 and st["exact_status"] >= 190
 
 
 def test_oracle_side_by_side_fresh_seed(lib, dev):
@@ -238,7 +239,7 @@ def test_tall_options_vs_oracle(lib, dev):
 def test_benchmark_table(lib, dev, tmp_path):
     st = cases.check_benchmark_table(lib, dev, tmp_path / "table.txt")
     print(st)
-    assert st["checked"] >= 60
+    assert st["instances"] == 58 and st["checked"] >= 130
 
 
 def test_compact_batched(lib, dev):
