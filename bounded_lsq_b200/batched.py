@@ -184,6 +184,8 @@ def solve_batched(lib, method, fun, jac, X0, lb, ub, ftol, xtol, gtol,
     # count[2] = problems still running after the last round (written by the
     # round kernel itself, blsq_round_batched `count`)
     count = torch.zeros(4, dtype=torch.int32, device=dev)
+    # BLSQ_ROUND_COUNT=0: count with the separate blsq_count_running launch
+    fused_count = os.environ.get("BLSQ_ROUND_COUNT", "1") != "0"
     # TRF: worklist of the problems that leave the Gauss-Newton shortcut
     # (blsq_round_batched `work`); BLSQ_TRF_TWO_KERNELS=0 -> single kernel
     rwork = None
@@ -297,11 +299,18 @@ def solve_batched(lib, method, fun, jac, X0, lb, ub, ftol, xtol, gtol,
                  float(ftol), float(xtol), float(gtol), max_nfev, first,
                  p_st, p_ist, p_xn, p_xj,
                  rwork_ptr if A >= TWO_KERNELS_ABOVE else None,
-                 count.data_ptr() if count_here else None, stream)
+                 count.data_ptr() if (count_here and fused_count) else None, stream)
         tock("round", t0, nrun)
         if timers is not None:
             timers["shape"] = (n, m, LS, S)
         launches += 2 if (rwork is None or A < TWO_KERNELS_ABOVE) else 3
+
+    def count_separately(A, idx32):
+        nonlocal launches
+        lib.call("blsq_count_running", A,
+                 None if idx32 is None else idx32.data_ptr(),
+                 istate.data_ptr(), count[2:].data_ptr(), lib.stream(X0))
+        launches += 1
 
     def graph_tail(A, idx, idx32, nrun):
         """The latency-sized tail of the batch (A <= tail_below slots, often a
@@ -343,6 +352,8 @@ def solve_batched(lib, method, fun, jac, X0, lb, ub, ftol, xtol, gtol,
                 try:
                     for _ in range(GRAPH_ROUNDS):
                         one_round(A, idx, idx32, 0, nrun)
+                    if not fused_count:
+                        count_separately(A, idx32)
                 finally:
                     if dbg:
                         tt.append(time.perf_counter())
@@ -411,6 +422,8 @@ def solve_batched(lib, method, fun, jac, X0, lb, ub, ftol, xtol, gtol,
         # bandwidth-sized, every 4th once they are launch-latency sized
         every = check_every if A > tail_below else max(check_every, 4)
         if rounds % every == 0 or rounds >= max_nfev:
+            if not fused_count:
+                count_separately(A, idx32)
             nrun = int(count[2].item())               # the one host sync
             if nrun == 0:
                 break

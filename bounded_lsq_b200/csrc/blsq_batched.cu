@@ -172,7 +172,16 @@ lin_kernel(int64_t A, const int32_t* __restrict__ idx, int m,
                 if (ok) {
                     if (MODE == 0) {
                         const double* rp = Jp + (int64_t)row * N;
-                        if (N % 2 == 0) {
+                        if (N % 4 == 0) {
+                            // 256-bit streaming loads: a whole 32-byte sector per
+                            // instruction and lane (rows of 4 / 8 doubles)
+#pragma unroll
+                            for (int j = 0; j < N; j += 4)
+                                asm volatile("ld.global.cs.v4.f64 {%0,%1,%2,%3}, [%4];"
+                                             : "=d"(a[s][j]), "=d"(a[s][j + 1]),
+                                               "=d"(a[s][j + 2]), "=d"(a[s][j + 3])
+                                             : "l"(rp + j));
+                        } else if (N % 2 == 0) {
 #pragma unroll
                             for (int j = 0; j < N; j += 2) {
                                 double2 t = __ldcs(reinterpret_cast<const double2*>(rp + j));
@@ -406,8 +415,17 @@ round_slot(int64_t slot, int64_t A, const int32_t* __restrict__ idx,
     return ist[IS_STATUS] == ST_RUNNING;
 }
 
+// CTAs per SM of the round kernel: TRF N <= 4 runs best at 4 x 128 threads
+// (128 registers; 3 x 164 without spills measured 5 % slower), dogbox and the
+// larger N at 3 (C3, N = 6 dogbox: 0.60 -> 0.50 ms per 10^6 problems).
+template <int N, int METHOD> struct RoundCfg {
+    static constexpr int MINB =
+        (METHOD == BLSQ_METHOD_DOGBOX || N > 4) ? (BLSQ_ROUND_MINB > 3 ? 3 : BLSQ_ROUND_MINB)
+                                                : BLSQ_ROUND_MINB;
+};
+
 template <int N, int METHOD, int MODE>
-__global__ void __launch_bounds__(BLSQ_ROUND_THREADS, BLSQ_ROUND_MINB)
+__global__ void __launch_bounds__(BLSQ_ROUND_THREADS, (RoundCfg<N, METHOD>::MINB))
 round_kernel(int64_t A, const int32_t* __restrict__ idx,
              const double* __restrict__ lin, const double* __restrict__ x0,
              const double* __restrict__ lb, const double* __restrict__ ub,

@@ -26,9 +26,13 @@ expdecay2_kernel(int64_t A, const int64_t* __restrict__ idx, int m,
     const double e2 = exp(-x.w * tr);
     F[g] = x.x * e1 + x.z * e2 - __ldcs(y + pid * m + r);
     if (J) {
-        double2* jp = reinterpret_cast<double2*>(J + g * 4);
-        __stcs(jp, make_double2(e1, -x.x * tr * e1));
-        __stcs(jp + 1, make_double2(e2, -x.z * tr * e2));
+        // one 256-bit streaming store per Jacobian row: a whole 32-byte sector
+        // per thread (two 128-bit stores wrote half sectors at a 32-byte
+        // stride, i.e. twice the write transactions)
+        const double j1 = -x.x * tr * e1, j3 = -x.z * tr * e2;
+        asm volatile("st.global.cs.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(J + g * 4), "d"(e1),
+                     "d"(j1), "d"(e2), "d"(j3)
+                     : "memory");
     }
 }
 

@@ -36,18 +36,25 @@ def _dist(group):
 
 
 class _Gather:
-    """All-gather of small per-rank records into a (nranks, k) tensor."""
+    """All-gather of small per-rank records into a preallocated (nranks, k)
+    tensor: ONE collective call, no list of outputs and no stack."""
 
     def __init__(self, group):
         self.group = group
         self.dist, self.nranks, self.rank = _dist(group)
+        self._out = {}
 
     def __call__(self, rec):
         if self.nranks == 1:
             return rec.view(1, -1)
-        parts = [torch.empty_like(rec) for _ in range(self.nranks)]
-        self.dist.all_gather(parts, rec.contiguous(), group=self.group)
-        return torch.stack(parts, 0).contiguous()
+        rec = rec.contiguous()
+        key = (rec.numel(), rec.dtype, rec.device)
+        out = self._out.get(key)
+        if out is None:
+            out = self._out[key] = torch.empty((self.nranks, rec.numel()),
+                                               dtype=rec.dtype, device=rec.device)
+        self.dist.all_gather_into_tensor(out.view(-1), rec.view(-1), group=self.group)
+        return out
 
     def sum_int(self, v, device):
         if self.nranks == 1:
@@ -262,6 +269,8 @@ def solve_tall(lib, method, fun, jac, x0, lb, ub, ftol, xtol, gtol, max_nfev,
         first = 0
         if trace is not None:
             trace(xnew_view.clone(), state, istate)
+        # (reading the status here instead of calling `fun` once more than the
+        # reference does: a 20 us look against a 1.5 ms callback at C4)
         status = int(istate[0].item())                   # host sync
         if status != L.STATUS_RUNNING:
             break

@@ -18,6 +18,10 @@ for step in "$@"; do
     smoke) python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${TAG}_smoke.log 2>&1; echo "smoke rc=$?"; tail -5 gpurun_out/${TAG}_smoke.log;;
     bench) k=$(echo "$arg" | tr -c 'a-zA-Z0-9' '_'); python bench.py $arg > gpurun_out/${TAG}_bench_${k}.json 2> gpurun_out/${TAG}_bench_${k}.err; echo "bench $arg rc=$?"; tail -c 1500 gpurun_out/${TAG}_bench_${k}.json; tail -5 gpurun_out/${TAG}_bench_${k}.err;;
     launches) ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file gpurun_out/${TAG}_launches_${arg}.csv python bench.py --workload $arg --steps 1 --warmup 1 --no-cpu-baseline --no-tall > gpurun_out/${TAG}_launches_${arg}.log 2>&1; echo "launches rc=$?";;
+    ncu) # ncu=<name>:<kernel regex>:<skip>:<count>:<python args>
+       IFS=: read -r nm rx skip cnt pyargs <<< "$arg"
+       ncu --set full --clock-control none --import-source on -k "regex:$rx" --launch-skip $skip --launch-count $cnt -o gpurun_out/${TAG}_${nm} -f python $pyargs > gpurun_out/${TAG}_ncu_${nm}.log 2>&1; echo "ncu $nm rc=$?"; tail -3 gpurun_out/${TAG}_ncu_${nm}.log;;
+    kbench) for l in $arg; do python tools/kbench.py --lib $l --workload c2; python tools/kbench.py --lib $l --workload c3; done > gpurun_out/${TAG}_kbench.log 2>&1; echo "kbench rc=$?"; cat gpurun_out/${TAG}_kbench.log;;
     py) python $arg > gpurun_out/${TAG}_$(basename $arg .py).log 2>&1; echo "py $arg rc=$?"; tail -30 gpurun_out/${TAG}_$(basename $arg .py).log;;
     sh) bash -c "$arg" > gpurun_out/${TAG}_sh.log 2>&1; echo "sh rc=$?"; tail -30 gpurun_out/${TAG}_sh.log;;
   esac
