@@ -22,6 +22,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <cstdio>
+#include <cstdlib>
 #include <utility>
 
 #include "../../include/blsq.h"
@@ -491,6 +493,385 @@ gram_kernel(int64_t m, int n, const double* __restrict__ J, const double* __rest
     }
 }
 
+// ===========================================================================
+// Pass 2 for 128 < n <= 256 (NB = 32): a CLUSTER of two CTAs per tile stream.
+//
+// The upper half of a 256 x 256 Gram matrix is 528 blocks of 8 x 8 = 263 KB of
+// FP64 accumulators, more than the register file of one SM: the one-CTA kernel
+// above spills by construction (12 KB of spill stores; 221 ms per 12.5 M rows,
+// 17 % of the FP64 peak).  Here the two CTAs of a cluster stream the same
+// 32-row tiles; each owns half of the Gram blocks (33 per warp, in registers)
+// and computes half of Y = J R1^-1, which it writes into BOTH CTAs' shared
+// memory (st.shared::cluster through DSMEM), so the triangular product that
+// dominates pass 2 is done once per tile, not once per CTA.
+//
+// Phase A, warp w of CTA c: column blocks j1 = 8 c + w and j2 = 31 - j1 of Y
+// for all four 8-row strips of the tile (2 j1 + 2 j2 + 4 = 66 k-chunks for
+// every warp: balanced), each R1^-1 fragment loaded ONCE per k-chunk from L2
+// (prefetched PF chunks ahead) and used for the four strips.
+// Hand-shake per tile, mbarriers in each CTA's shared memory:
+//   yfree[0] (CW arrivals)  my warps have finished phase B of the last tile
+//   yfree[1] (CW arrivals)  the PEER's warps have (remote arrive)
+//   yready   (2 CW)         all 16 warps of the cluster have stored their part
+//                           of Y into MY buffer
+// ===========================================================================
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t saddr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void st_cluster_f64(uint32_t addr, double v) {
+    asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(addr)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAITC_%=:\n"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONEC_%=;\n"
+        "bra WAITC_%=;\n"
+        "DONEC_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n"
+                 "barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+
+// Gram blocks of one role with the fragments taken straight from shared memory
+// (base[8 b] = element of column block b for this lane): holding all 32
+// fragments of a k-chunk in registers next to 33 accumulator pairs spills.
+template <int NB, int Q0, int... Qs>
+__device__ __forceinline__ void mma_role_blocks_lazy(double (&acc)[sizeof...(Qs)][2],
+                                                     const double* __restrict__ base,
+                                                     std::integer_sequence<int, Qs...>) {
+    (dmma(acc[Qs], base[8 * Tri<NB>::row(Q0 + Qs)], base[8 * Tri<NB>::col(Q0 + Qs)]), ...);
+}
+
+struct Gram2C {
+    static constexpr int NB = 32, T = 32, S = 2, CW = 8, W = 256, QR = T / 4;
+    static constexpr int QS = QR * W + 4;
+    static constexpr int NBLK = Tri<NB>::COUNT;                 // 528
+    static constexpr int ROLES = 16;                            // 8 per CTA
+    // 33 Gram blocks per warp.  The vector work is spread too: warp w of CTA 0
+    // accumulates Y^T f, warp w of CTA 1 J^T f, each for the column blocks
+    // b = w, w + 8, w + 16, w + 24 (one warp holding all 2 x 32 partial sums
+    // spilled them); f.f by warp 0 of CTA 0.
+    static constexpr int BPR = NBLK / ROLES;                    // 33
+    static_assert(BPR * ROLES == NBLK, "528 = 16 x 33");
+    __host__ __device__ static constexpr int role_begin(int r) { return r * BPR; }
+    __host__ __device__ static constexpr int role_count(int r) { return BPR; }
+    // NO producer warp: with 9 warps one SM sub-partition hosts three and the
+    // register limit is 168 per thread; 33 accumulator pairs are 132 of them
+    // and phase A needs ~60 more.  With 8 warps (two per sub-partition) the
+    // limit is 255 and nothing spills; warp 0 issues the bulk copies of the
+    // NEXT tile at the top of every iteration instead.
+    static constexpr int THREADS = CW * 32;
+    static constexpr int STAGE_DOUBLES = 4 * QS + T;
+    static constexpr int RING_DOUBLES = S * STAGE_DOUBLES;
+    static constexpr int YBUF_DOUBLES = 4 * QS;
+    static constexpr int MAIN_DOUBLES = RING_DOUBLES + YBUF_DOUBLES;
+    static constexpr int NBAR = 2 * S + 3;
+    static constexpr size_t SMEM_BYTES = (size_t)MAIN_DOUBLES * 8 + NBAR * 8 + 16;
+    static constexpr int OFF_V1 = W * W, OFF_FF = W * W + W, OFF_V2 = W * W + W + 2;
+    static constexpr int REC = W * W + 2 * W + 2;
+    static constexpr int PF = 4;                                // R1^-1 prefetch distance
+};
+
+// warp 0 of each CTA: start the copies of tile `job` into ring stage `stage`
+template <bool EXACT>
+__device__ __forceinline__ void gram2c_issue(int64_t job, int stage, int64_t m, int n,
+                                             const double* __restrict__ J,
+                                             const double* __restrict__ f, double* smem,
+                                             uint64_t* full) {
+    typedef Gram2C L;
+    constexpr int T = L::T, QR = L::QR, QS = L::QS, W = L::W;
+    const int lane = threadIdx.x & 31;
+    const int RS = EXACT ? W : n;
+    const int64_t row0 = job * T;
+    const int rows = (m - row0 < T) ? (int)(m - row0) : T;
+    double* dj = smem + (size_t)stage * L::STAGE_DOUBLES;
+    double* df = dj + 4 * QS;
+    if (rows == T) {
+        const uint32_t q_bytes = (uint32_t)(QR * n) * 8u;
+        if (lane == 0) mbar_expect_tx(&full[stage], 4u * q_bytes + T * 8u);
+        __syncwarp();
+        if (lane < 4)
+            bulk_g2s(dj + lane * QS, J + (row0 + lane * QR) * n, q_bytes, &full[stage]);
+        else if (lane == 4)
+            bulk_g2s(df, f + row0, T * 8u, &full[stage]);
+    } else {
+        // ragged last tile: plain loads, rows past m are zero
+        for (int e = lane; e < T * n; e += 32) {
+            const int r = e / n, c = e % n;
+            dj[(r / QR) * QS + (r % QR) * RS + c] = (r < rows) ? J[(row0 + r) * n + c] : 0.0;
+        }
+        for (int r = lane; r < T; r += 32) df[r] = (r < rows) ? f[row0 + r] : 0.0;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full[stage]);
+    }
+    __syncwarp();
+}
+
+// phase B of one role: its 33 Gram blocks (static block list, accumulators in
+// the shared `acc` array) from the Y tile in shared memory
+template <int ROLE>
+__device__ __forceinline__ void gram2c_blocks(double (&acc)[Gram2C::BPR][2],
+                                              const double* __restrict__ base) {
+    mma_role_blocks_lazy<Gram2C::NB, ROLE * Gram2C::BPR>(
+        acc, base, std::make_integer_sequence<int, Gram2C::BPR>{});
+}
+template <int... ROLES_>
+__device__ __forceinline__ void gram2c_blocks_dispatch(int role, double (&acc)[Gram2C::BPR][2],
+                                                       const double* __restrict__ base,
+                                                       std::integer_sequence<int, ROLES_...>) {
+    ((role == ROLES_ ? (gram2c_blocks<ROLES_>(acc, base), 0) : 0), ...);
+}
+template <int ROLE>
+__device__ __forceinline__ void gram2c_store(const double (&acc)[Gram2C::BPR][2],
+                                             double* __restrict__ rec, int lr, int lc) {
+    constexpr int NB = Gram2C::NB, W = Gram2C::W, Q0 = ROLE * Gram2C::BPR;
+#pragma unroll
+    for (int q = 0; q < Gram2C::BPR; q++) {
+        const int bi = Tri<NB>::row(Q0 + q), bj = Tri<NB>::col(Q0 + q);
+        double* dst = rec + (size_t)(8 * bi + lr) * W + 8 * bj + 2 * lc;
+        *reinterpret_cast<double2*>(dst) = make_double2(acc[q][0], acc[q][1]);
+    }
+}
+template <int... ROLES_>
+__device__ __forceinline__ void gram2c_store_dispatch(int role,
+                                                      const double (&acc)[Gram2C::BPR][2],
+                                                      double* __restrict__ rec, int lr, int lc,
+                                                      std::integer_sequence<int, ROLES_...>) {
+    ((role == ROLES_ ? (gram2c_store<ROLES_>(acc, rec, lr, lc), 0) : 0), ...);
+}
+
+// The tile loop of one consumer warp.  Everything except the Gram-block list of
+// phase B is the SAME code for all sixteen roles (one copy in the instruction
+// cache: with a body per role the warps stalled on instruction fetch, 4.2 of
+// 15 stall cycles per issue in the first version).
+template <bool EXACT>
+__device__ __forceinline__ void gram2c_consumer(int role, int64_t njobs, int64_t job0,
+                                                int64_t jstride, int64_t m,
+                                                const double* __restrict__ J,
+                                                const double* __restrict__ f,
+                                                const double* __restrict__ rinvp, int n,
+                                                double* smem, uint64_t* full, uint64_t* empty,
+                                                uint64_t* yfree, uint64_t* yready,
+                                                double* __restrict__ rec, uint32_t crank) {
+    typedef Gram2C L;
+    constexpr int NB = L::NB, S = L::S, W = L::W, QR = L::QR, QS = L::QS, PF = L::PF;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int lr = lane >> 2, lc = lane & 3;
+    const int RS = EXACT ? W : n;
+    double* ybuf = smem + L::RING_DOUBLES;
+    const uint32_t peer = crank ^ 1u;
+    const uint32_t ybuf_peer = map_to_cta(smem_u32(ybuf), peer);
+    const uint32_t yready_peer = map_to_cta(smem_u32(yready), peer);
+    const uint32_t yready_self = map_to_cta(smem_u32(yready), crank);
+    const uint32_t yfree0_self = map_to_cta(smem_u32(yfree), crank);
+    const uint32_t yfree1_peer = map_to_cta(smem_u32(yfree + 1), peer);
+    // this warp's two column blocks of Y
+    const int j1 = (int)crank * 8 + warp, j2 = NB - 1 - j1;
+    const int kmax = 2 * j2 + 2, k1max = 2 * j1 + 2;
+    const bool cta0 = crank == 0;
+
+    double acc[L::BPR][2];
+#pragma unroll
+    for (int q = 0; q < L::BPR; q++) { acc[q][0] = 0.0; acc[q][1] = 0.0; }
+    double gv[4] = {0.0, 0.0, 0.0, 0.0}, ff = 0.0;   // Y^T f (CTA 0) or J^T f (CTA 1)
+    // R1^-1 half fragment of block (kc >> 1, j), k-half kc & 1, for this lane
+    auto rin = [&](int kc, int j) -> const double* {
+        const int kb = kc >> 1;
+        const int q = kb * NB - (kb * (kb - 1)) / 2 + (j - kb);
+        return rinvp + (size_t)(q * 2 + (kc & 1)) * 32 + lane;
+    };
+
+    int stage = 0;
+    uint32_t phase = 0, yphase = 0;
+    uint32_t ephase[2] = {0u, 0u};        // warp 0: completed uses of each ring stage
+    if (warp == 0 && job0 < njobs) gram2c_issue<EXACT>(job0, 0, m, n, J, f, smem, full);
+    for (int64_t t = job0; t < njobs; t += jstride) {
+        if (warp == 0 && t + jstride < njobs) {
+            // the other stage is free once all eight warps have left the tile
+            // before this one (its first use needs no wait)
+            const int ns = stage ^ 1;
+            if (t != job0) { mbar_wait(&empty[ns], ephase[ns]); ephase[ns] ^= 1u; }
+            gram2c_issue<EXACT>(t + jstride, ns, m, n, J, f, smem, full);
+        }
+        mbar_wait(&full[stage], phase);
+        const double* tj = smem + (size_t)stage * L::STAGE_DOUBLES;
+        const double* tf = tj + 4 * QS;
+        // ---- phase A: my two column blocks of Y for the four strips ----
+        double y1[4][2], y2[4][2];
+#pragma unroll
+        for (int s = 0; s < 4; s++) { y1[s][0] = y1[s][1] = y2[s][0] = y2[s][1] = 0.0; }
+        const double* arow = tj + (lr & 3) * QS + (lr >> 2) * RS + lc;   // strip s: + 2 s RS
+        double b2[PF], b1[PF];
+#pragma unroll
+        for (int u = 0; u < PF; u++) {
+            b2[u] = (u < kmax) ? __ldg(rin(u, j2)) : 0.0;
+            b1[u] = (u < k1max) ? __ldg(rin(u, j1)) : 0.0;
+        }
+#pragma unroll 1
+        for (int kc0 = 0; kc0 < kmax; kc0 += PF) {
+#pragma unroll
+            for (int u = 0; u < PF; u++) {
+                const int kc = kc0 + u;
+                if (kc < kmax) {
+                    const bool in = EXACT || kc * 4 + lc < n;
+                    double a[4];
+#pragma unroll
+                    for (int s = 0; s < 4; s++) a[s] = in ? arow[2 * s * RS + kc * 4] : 0.0;
+                    const double bb2 = b2[u], bb1 = b1[u];
+                    const int kn = kc + PF;
+                    b2[u] = (kn < kmax) ? __ldg(rin(kn, j2)) : 0.0;
+                    b1[u] = (kn < k1max) ? __ldg(rin(kn, j1)) : 0.0;
+#pragma unroll
+                    for (int s = 0; s < 4; s++) dmma(y2[s], a[s], bb2);
+                    if (kc < k1max) {
+#pragma unroll
+                        for (int s = 0; s < 4; s++) dmma(y1[s], a[s], bb1);
+                    }
+                }
+            }
+        }
+        if (!cta0) {
+            // J^T f of my column blocks straight from the raw tile (trf.py:244)
+#pragma unroll 1
+            for (int kc = 0; kc < QR; kc++) {
+                const double fk = tf[lc * QR + kc];
+                const double* rawb = tj + lc * QS + kc * RS + lr;
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const int b = warp + 8 * i;
+                    const double raw = (EXACT || 8 * b + lr < n) ? rawb[8 * b] : 0.0;
+                    gv[i] = fma(raw, fk, gv[i]);
+                }
+            }
+        }
+        // everyone (both CTAs) is done reading the Y buffers of the last tile
+        mbar_wait_cluster(&yfree[0], yphase ^ 1);
+        mbar_wait_cluster(&yfree[1], yphase ^ 1);
+        {
+            const int odd = lr & 1;
+#pragma unroll
+            for (int s = 0; s < 4; s++) {
+                const int off = (lr & 3) * QS + (2 * s + (lr >> 2)) * W + 2 * lc;
+                double* yl = ybuf + off;
+                const uint32_t yp = ybuf_peer + (uint32_t)off * 8u;
+                // element order swapped on odd rows (bank conflicts, see above)
+                const double v1a = odd ? y1[s][1] : y1[s][0], v1b = odd ? y1[s][0] : y1[s][1];
+                const double v2a = odd ? y2[s][1] : y2[s][0], v2b = odd ? y2[s][0] : y2[s][1];
+                yl[8 * j1 + odd] = v1a;
+                yl[8 * j1 + 1 - odd] = v1b;
+                yl[8 * j2 + odd] = v2a;
+                yl[8 * j2 + 1 - odd] = v2b;
+                st_cluster_f64(yp + (uint32_t)(8 * j1 + odd) * 8u, v1a);
+                st_cluster_f64(yp + (uint32_t)(8 * j1 + 1 - odd) * 8u, v1b);
+                st_cluster_f64(yp + (uint32_t)(8 * j2 + odd) * 8u, v2a);
+                st_cluster_f64(yp + (uint32_t)(8 * j2 + 1 - odd) * 8u, v2b);
+            }
+        }
+        // the lanes' stores are ordered before lane 0's release-arrive by the
+        // warp barrier (cumulativity); no separate cluster fence
+        __syncwarp();
+        if (lane == 0) {
+            mbar_arrive_cluster(yready_self);
+            mbar_arrive_cluster(yready_peer);
+        }
+        mbar_wait_cluster(yready, yphase);
+        // ---- phase B: my Gram blocks += Y^T Y (block list by role) ----
+#pragma unroll 1
+        for (int kc = 0; kc < QR; kc++) {
+            const double* base = ybuf + lc * QS + kc * W + lr;
+            gram2c_blocks_dispatch(role, acc, base, std::make_integer_sequence<int, L::ROLES>{});
+            if (cta0) {
+                const double fk = tf[lc * QR + kc];
+#pragma unroll
+                for (int i = 0; i < 4; i++) gv[i] = fma(base[8 * (warp + 8 * i)], fk, gv[i]);
+                if (warp == 0 && lr == 0) ff = fma(fk, fk, ff);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) {
+            mbar_arrive(&empty[stage]);
+            mbar_arrive_cluster(yfree0_self);      // my yfree[0]
+            mbar_arrive_cluster(yfree1_peer);      // the peer's yfree[1]
+        }
+        if (++stage == S) { stage = 0; phase ^= 1; }
+        yphase ^= 1;
+    }
+    // ---- this CTA's record: its half of the Gram blocks, its vector part ----
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        gv[i] += __shfl_xor_sync(0xffffffffu, gv[i], 1);
+        gv[i] += __shfl_xor_sync(0xffffffffu, gv[i], 2);
+    }
+    ff += __shfl_xor_sync(0xffffffffu, ff, 1);
+    ff += __shfl_xor_sync(0xffffffffu, ff, 2);
+    gram2c_store_dispatch(role, acc, rec, lr, lc, std::make_integer_sequence<int, L::ROLES>{});
+    if (lc == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            rec[(cta0 ? L::OFF_V1 : L::OFF_V2) + 8 * (warp + 8 * i) + lr] = gv[i];
+    }
+    if (cta0 && warp == 0 && lane == 0) rec[L::OFF_FF] = ff;
+}
+
+template <bool EXACT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Gram2C::THREADS, 1)
+gram2c_kernel(int64_t m, int n, const double* __restrict__ J, const double* __restrict__ f,
+              const double* __restrict__ rinvp, double* __restrict__ partial) {
+    typedef Gram2C L;
+    constexpr int T = L::T, S = L::S, CW = L::CW, W = L::W, QR = L::QR, QS = L::QS;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* smem = reinterpret_cast<double*>(smem_raw);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + L::MAIN_DOUBLES);
+    uint64_t* empty = full + S;
+    uint64_t* yfree = empty + S;          // [0] mine, [1] the peer's readers
+    uint64_t* yready = yfree + 2;
+    const int warp = threadIdx.x >> 5;
+    const uint32_t crank = cluster_ctarank();
+    double* rec = partial + (size_t)blockIdx.x * L::REC;
+
+    for (int i = threadIdx.x; i < L::MAIN_DOUBLES; i += L::THREADS) smem[i] = 0.0;
+    for (int i = threadIdx.x; i < L::REC; i += L::THREADS) rec[i] = 0.0;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; s++) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], CW);
+        }
+        mbar_init(&yfree[0], CW);
+        mbar_init(&yfree[1], CW);
+        mbar_init(yready, 2 * CW);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();                   // the peer's barriers exist before any remote arrive
+
+    const int64_t njobs = (m + T - 1) / T;
+    const int64_t job0 = blockIdx.x >> 1, jstride = gridDim.x >> 1;
+    gram2c_consumer<EXACT>((int)crank * CW + warp, njobs, job0, jstride, m, J, f, rinvp, n, smem,
+                           full, empty, yfree, yready, rec, crank);
+    // neither CTA may exit while the other can still write into its shared memory
+    __syncthreads();
+    cluster_sync_all();
+}
+
 // out (blsq_tall_record_size(n) doubles): G (n x n row-major, upper triangle
 // valid) | Y^T f (n) | f.f | J^T f (n)  = sum over the P per-CTA records, in
 // CTA order.
@@ -581,9 +962,53 @@ int launch_gram_e(int64_t m, int n, const double* J, const double* f, const doub
     return 0;
 }
 
+template <bool EXACT>
+int launch_gram2c(int64_t m, int n, const double* J, const double* f, const double* rinvp,
+                  double* work, double* out, cudaStream_t s) {
+    typedef Gram2C L;
+    cudaError_t e = cudaFuncSetAttribute(gram2c_kernel<EXACT>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)L::SMEM_BYTES);
+    if (e != cudaSuccess) return (int)e;
+    // clusters that can be resident at once (a GPC with an odd number of free
+    // SMs leaves one without a partner): persistent CTAs, so no more than that
+    static int max_clusters = 0;
+    if (max_clusters == 0) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * 74, 1, 1);
+        cfg.blockDim = dim3(L::THREADS, 1, 1);
+        cfg.dynamicSmemBytes = L::SMEM_BYTES;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        int nc = 0;
+        if (cudaOccupancyMaxActiveClusters(&nc, gram2c_kernel<EXACT>, &cfg) != cudaSuccess || nc < 1)
+            nc = sm_count() / 2 - 4;
+        (void)cudaGetLastError();
+        max_clusters = nc;
+        if (getenv("BLSQ_DEBUG")) fprintf(stderr, "# gram2c: max active clusters %d\n", nc);
+    }
+    const int64_t ntiles = (m + L::T - 1) / L::T;
+    int clusters = (int)(ntiles < max_clusters ? (ntiles > 0 ? ntiles : 1) : max_clusters);
+    const int grid = 2 * clusters;
+    gram2c_kernel<EXACT><<<grid, L::THREADS, L::SMEM_BYTES, s>>>(m, n, J, f, rinvp, work);
+    BLSQ_LAUNCH_CHECK();
+    const int total = n * n + 2 * n + 1;
+    gram_reduce_kernel<<<(total + 255) / 256, 256, 0, s>>>(grid, L::W, L::REC, n, work, out);
+    BLSQ_LAUNCH_CHECK();
+    return 0;
+}
+
 template <int NB, int PASS>
 int launch_gram(int64_t m, int n, const double* J, const double* f, const double* rinvp,
                 int sstride, double* work, double* out, cudaStream_t s) {
+#ifndef BLSQ_NO_GRAM2C
+    if (NB == 32 && PASS == 2) {
+        if (n == 256) return launch_gram2c<true>(m, n, J, f, rinvp, work, out, s);
+        return launch_gram2c<false>(m, n, J, f, rinvp, work, out, s);
+    }
+#endif
     if (n == 8 * NB)
         return launch_gram_e<NB, PASS, true>(m, n, J, f, rinvp, sstride, work, out, s);
     return launch_gram_e<NB, PASS, false>(m, n, J, f, rinvp, sstride, work, out, s);

@@ -39,6 +39,11 @@ KEYS = [
     "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
     "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio",
     "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_membar_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio",
+    "smsp__pipe_tensor_subpipe_dmma_cycles_active.avg.pct_of_peak_sustained_active",
+    "launch__cluster_size", "launch__cluster_max_active",
     "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
     "local_load_bytes", "smsp__inst_executed_op_local_ld.sum",
     "smsp__inst_executed_op_local_st.sum",

@@ -165,10 +165,21 @@ if __name__ == "__main__":
     ap.add_argument("--time", action="store_true")
     ap.add_argument("--round", action="store_true", help="latency of the tail kernel")
     ap.add_argument("--round-n", type=int, default=0)
+    ap.add_argument("--n256", action="store_true", help="n = 256 / 200 / 130 only")
+    ap.add_argument("--time256", action="store_true", help="n = 256 timing only")
     ap.add_argument("--quick", action="store_true",
                     help="one correctness case + the n = 64 timing (variant sweeps)")
     a = ap.parse_args()
     lib = get_lib()
+    if a.time256:
+        timing(lib, 1 << 20, 256, reps=3)
+        sys.exit(0)
+    if a.n256:
+        check(lib, 30000, 256, 1e2, 1)
+        check(lib, 9000, 200, 10.0, 2)
+        check(lib, 5003, 130, 10.0, 1)
+        timing(lib, 1 << 20, 256, reps=3)
+        sys.exit(0)
     if a.quick:
         print("lib", lib.path)
         check(lib, 1 << 20, 64, 1e3, 2, 4)
