@@ -582,13 +582,17 @@ struct Gram2C {
     static constexpr int STAGE_DOUBLES = 4 * QS + T;
     static constexpr int RING_DOUBLES = S * STAGE_DOUBLES;
     static constexpr int YBUF_DOUBLES = 4 * QS;
-    static constexpr int MAIN_DOUBLES = RING_DOUBLES + YBUF_DOUBLES;
+    // per-warp ring of R1^-1 half fragments (2 per k-chunk: column blocks j2, j1),
+    // filled by cp.async RB - 1 k-chunks ahead of their use
+    static constexpr int RB = 6;
+    static constexpr int BRING_DOUBLES = CW * RB * 2 * 32;
+    static constexpr int MAIN_DOUBLES = RING_DOUBLES + YBUF_DOUBLES + BRING_DOUBLES;
     static constexpr int NBAR = 2 * S + 3;
     static constexpr size_t SMEM_BYTES = (size_t)MAIN_DOUBLES * 8 + NBAR * 8 + 16;
     static constexpr int OFF_V1 = W * W, OFF_FF = W * W + W, OFF_V2 = W * W + W + 2;
     static constexpr int REC = W * W + 2 * W + 2;
-    static constexpr int PF = 4;                                // R1^-1 prefetch distance
 };
+static_assert(Gram2C::SMEM_BYTES <= 232448, "gram2c shared memory");
 
 // warp 0 of each CTA: start the copies of tile `job` into ring stage `stage`
 template <bool EXACT>
@@ -672,11 +676,13 @@ __device__ __forceinline__ void gram2c_consumer(int role, int64_t njobs, int64_t
                                                 uint64_t* yfree, uint64_t* yready,
                                                 double* __restrict__ rec, uint32_t crank) {
     typedef Gram2C L;
-    constexpr int NB = L::NB, S = L::S, W = L::W, QR = L::QR, QS = L::QS, PF = L::PF;
+    constexpr int NB = L::NB, S = L::S, W = L::W, QR = L::QR, QS = L::QS, RB = L::RB;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int lr = lane >> 2, lc = lane & 3;
     const int RS = EXACT ? W : n;
     double* ybuf = smem + L::RING_DOUBLES;
+    const double* bring = smem + L::RING_DOUBLES + L::YBUF_DOUBLES + warp * (RB * 2 * 32) + lane;
+    const uint32_t bring_s = smem_u32(bring);
     const uint32_t peer = crank ^ 1u;
     const uint32_t ybuf_peer = map_to_cta(smem_u32(ybuf), peer);
     const uint32_t yready_peer = map_to_cta(smem_u32(yready), peer);
@@ -719,35 +725,48 @@ __device__ __forceinline__ void gram2c_consumer(int role, int64_t njobs, int64_t
 #pragma unroll
         for (int s = 0; s < 4; s++) { y1[s][0] = y1[s][1] = y2[s][0] = y2[s][1] = 0.0; }
         const double* arow = tj + (lr & 3) * QS + (lr >> 2) * RS + lc;   // strip s: + 2 s RS
-        double b2[PF], b1[PF];
+        // R1^-1 fragments: every lane copies its own element of the two half
+        // fragments of k-chunk kn into ring slot kn % RB (and reads only that
+        // element back: no cross-lane hand-over), one cp.async group per k-chunk
+        auto fetch = [&](int kn) {
+            const int slot = kn % RB;
+            if (kn < kmax)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(
+                                 bring_s + (uint32_t)(slot * 2 * 32) * 8u),
+                             "l"(rin(kn, j2))
+                             : "memory");
+            if (kn < k1max)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(
+                                 bring_s + (uint32_t)((slot * 2 + 1) * 32) * 8u),
+                             "l"(rin(kn, j1))
+                             : "memory");
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
 #pragma unroll
-        for (int u = 0; u < PF; u++) {
-            b2[u] = (u < kmax) ? __ldg(rin(u, j2)) : 0.0;
-            b1[u] = (u < k1max) ? __ldg(rin(u, j1)) : 0.0;
-        }
-#pragma unroll 1
-        for (int kc0 = 0; kc0 < kmax; kc0 += PF) {
+        for (int u = 0; u < RB - 1; u++) fetch(u);
+#pragma unroll 2
+        for (int kc = 0; kc < kmax; kc++) {
+            // groups 0 .. kc + RB - 2 are committed: chunk kc has landed when at
+            // most RB - 2 of them are pending
+            asm volatile("cp.async.wait_group %0;" ::"n"(RB - 2) : "memory");
+            const int slot = kc % RB;
+            const double bb2 = bring[slot * 2 * 32];
+            const double bb1 = (kc < k1max) ? bring[(slot * 2 + 1) * 32] : 0.0;
+            const bool in = EXACT || kc * 4 + lc < n;
+            double a[4];
 #pragma unroll
-            for (int u = 0; u < PF; u++) {
-                const int kc = kc0 + u;
-                if (kc < kmax) {
-                    const bool in = EXACT || kc * 4 + lc < n;
-                    double a[4];
+            for (int s = 0; s < 4; s++) a[s] = in ? arow[2 * s * RS + kc * 4] : 0.0;
+            // refill the slot of chunk kc - 1 (its values were consumed by the
+            // DMMAs of the last iteration)
+            fetch(kc + RB - 1);
 #pragma unroll
-                    for (int s = 0; s < 4; s++) a[s] = in ? arow[2 * s * RS + kc * 4] : 0.0;
-                    const double bb2 = b2[u], bb1 = b1[u];
-                    const int kn = kc + PF;
-                    b2[u] = (kn < kmax) ? __ldg(rin(kn, j2)) : 0.0;
-                    b1[u] = (kn < k1max) ? __ldg(rin(kn, j1)) : 0.0;
+            for (int s = 0; s < 4; s++) dmma(y2[s], a[s], bb2);
+            if (kc < k1max) {
 #pragma unroll
-                    for (int s = 0; s < 4; s++) dmma(y2[s], a[s], bb2);
-                    if (kc < k1max) {
-#pragma unroll
-                        for (int s = 0; s < 4; s++) dmma(y1[s], a[s], bb1);
-                    }
-                }
+                for (int s = 0; s < 4; s++) dmma(y1[s], a[s], bb1);
             }
         }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
         if (!cta0) {
             // J^T f of my column blocks straight from the raw tile (trf.py:244)
 #pragma unroll 1
