@@ -31,6 +31,7 @@ SIGNATURES = {
     "blsq_scaling_vector": [_l, _i, _p, _p, _p, _p, _i, _p, _p, _p],
     "blsq_in_bounds": [_l, _i, _p, _p, _p, _i, _p, _p],
     "blsq_find_intersection": [_l, _i, _p, _p, _p, _p, _i, _p, _p, _p, _p],
+    "blsq_covariance": [_l, _i, _p, _l, _i, _i, _p, _p],
     "blsq_fd2_points": [_l, _p, _i, _p, _p, _p, _i, _d, _p, _p, _p],
     "blsq_fd3_points": [_l, _p, _i, _p, _p, _p, _i, _d, _p, _p, _p],
     "blsq_compact_batched": [_l, _p, _p, _i, _p, _p, _p, _p, _p, _p, _p, _p],
@@ -160,7 +161,9 @@ class Lib:
             raise BlsqError(f"blsq_state_layout({method}, {n}) failed: {rc}")
         keys = ("size", "x", "x_new", "scale", "obj", "delta", "gnorm", "g",
                 "alpha")
-        return dict(zip(keys, list(out)))
+        d = dict(zip(keys, list(out)))
+        d["R"] = d["g"] - n - n * (n + 1) // 2          # R | Q^T f | g are contiguous
+        return d
 
     def tall_layout(self, n):
         out = (C.c_int64 * 17)()

@@ -142,7 +142,7 @@ def solve_batched(lib, method, fun, jac, X0, lb, ub, ftol, xtol, gtol,
                   max_nfev, scaling, diff_step=None, check_every=1,
                   compact_below=0.75, tail_below=8192, trace=None,
                   timers=None, graph_tail_rounds=None, prologue=None,
-                  prologue_rounds=6):
+                  prologue_rounds=6, x_covariance=False):
     """Run ``method`` ('trf' | 'dogbox') on B problems.
 
     fun(X, idx) -> (A, m); jac is a callable jac(X, idx) -> (A, m, n) or the
@@ -493,7 +493,14 @@ def solve_batched(lib, method, fun, jac, X0, lb, ub, ftol, xtol, gtol,
         mask = torch.empty((B, n), dtype=torch.int64, device=dev)
         lib.call("blsq_dogbox_on_bound", B, n, istate.data_ptr(),
                  mask.data_ptr(), stream)
+    cov = None
+    if x_covariance:
+        # (J^T J)^-1 at the returned x from the triangle the solve holds
+        cov = torch.empty((B, n, n), dtype=f64, device=dev)
+        lib.call("blsq_covariance", B, n, state.data_ptr(), S, lay["R"], 1,
+                 cov.data_ptr(), stream)
     return dict(
+        x_covariance=cov,
         x=x, obj_value=state[:, lay["obj"]].clone(),
         optimality=state[:, lay["gnorm"]].clone(), active_mask=mask,
         nfev=istate[:, 1].to(torch.int64), njev=istate[:, 2].to(torch.int64),

@@ -225,6 +225,55 @@ __global__ void fd3_points_kernel(int64_t A, const int32_t* __restrict__ idx,
 
 }  // namespace
 
+// x_covariance (least_squares.py:248-252: the inverse of J^T J) from the
+// triangular factor J = Q R that the solve already holds: (R^T R)^-1 =
+// R^-1 R^-T.  One thread per problem, R given as the packed upper triangle
+// (row i holds columns i..n-1) at `r_off` of a record of `stride` doubles, or
+// dense row-major (packed = 0).  A zero pivot ("the inverse doesn't exist")
+// gives a NaN matrix.
+__global__ void covariance_kernel(int64_t B, int n, const double* __restrict__ rec,
+                                  int64_t stride, int r_off, int packed,
+                                  double* __restrict__ cov) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const double* R = rec + b * stride + r_off;
+    double* C = cov + b * (int64_t)n * n;
+    auto r = [&](int i, int j) -> double {
+        return packed ? R[i * n - (i * (i - 1)) / 2 + (j - i)] : R[(int64_t)i * n + j];
+    };
+    bool singular = false;
+    for (int i = 0; i < n; i++) singular = singular || !(r(i, i) != 0.0);
+    if (singular) {
+        for (int e = 0; e < n * n; e++) C[e] = nan("");
+        return;
+    }
+    // T = R^-1 (upper) stored in C, column by column (back substitution)
+    for (int j = 0; j < n; j++) {
+        for (int i = n - 1; i >= 0; i--) {
+            double v = 0.0;
+            if (i == j) v = 1.0 / r(i, i);
+            else if (i < j) {
+                double acc = 0.0;
+                for (int k = i + 1; k <= j; k++) acc = fma(r(i, k), C[(int64_t)k * n + j], acc);
+                v = -acc / r(i, i);
+            }
+            C[(int64_t)i * n + j] = v;
+        }
+    }
+    // C = T T^T in place, row by row from the top: entry (i, j), i <= j, needs
+    // rows i and j of T from column j on, which are not overwritten yet when
+    // the lower triangle is filled by symmetry afterwards
+    for (int i = 0; i < n; i++) {
+        for (int j = i; j < n; j++) {
+            double acc = 0.0;
+            for (int k = j; k < n; k++) acc = fma(C[(int64_t)i * n + k], C[(int64_t)j * n + k], acc);
+            C[(int64_t)i * n + j] = acc;          // (i, j) is read no more: k >= j > ... only later columns
+        }
+    }
+    for (int i = 0; i < n; i++)
+        for (int j = 0; j < i; j++) C[(int64_t)i * n + j] = C[(int64_t)j * n + i];
+}
+
 extern "C" {
 
 int blsq_version(void) { return BLSQ_VERSION; }
@@ -337,6 +386,17 @@ int blsq_fd3_points(int64_t A, const int32_t* idx, int n, const double* x,
     int64_t total = A * n * n;
     fd3_points_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         A, idx, n, x, lb, ub, bstride, rel_step, Xp, dxo);
+    BLSQ_LAUNCH_CHECK();
+    return 0;
+}
+
+int blsq_covariance(int64_t B, int n, const double* rec, int64_t stride, int r_off,
+                    int packed, double* cov, void* stream) {
+    if (B < 0 || n < 1 || n > 256 || !rec || !cov || stride < 0 || r_off < 0) return BLSQ_E_BADARG;
+    if (B == 0) return 0;
+    int64_t blocks = (B + 127) / 128;
+    covariance_kernel<<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>(B, n, rec, stride, r_off,
+                                                                          packed, cov);
     BLSQ_LAUNCH_CHECK();
     return 0;
 }

@@ -561,7 +561,7 @@ __device__ __forceinline__ void mma_role_blocks_lazy(double (&acc)[sizeof...(Qs)
 }
 
 struct Gram2C {
-    static constexpr int NB = 32, T = 32, S = 2, CW = 8, W = 256, QR = T / 4;
+    static constexpr int NB = 32, T = 32, S = 1, CW = 8, W = 256, QR = T / 4;
     static constexpr int QS = QR * W + 4;
     static constexpr int NBLK = Tri<NB>::COUNT;                 // 528
     static constexpr int ROLES = 16;                            // 8 per CTA
@@ -581,13 +581,17 @@ struct Gram2C {
     static constexpr int THREADS = CW * 32;
     static constexpr int STAGE_DOUBLES = 4 * QS + T;
     static constexpr int RING_DOUBLES = S * STAGE_DOUBLES;
-    static constexpr int YBUF_DOUBLES = 4 * QS;
+    // ONE stage for the J tile (it is only read in phase A; the copy of the
+    // next tile is issued as soon as all warps are past it and lands during
+    // phase B) and TWO Y buffers: phase A of tile t + 1 does not wait for the
+    // slowest reader of tile t.
+    static constexpr int YBUF_DOUBLES = 2 * 4 * QS;
     // per-warp ring of R1^-1 half fragments (2 per k-chunk: column blocks j2, j1),
     // filled by cp.async RB - 1 k-chunks ahead of their use
     static constexpr int RB = 6;
     static constexpr int BRING_DOUBLES = CW * RB * 2 * 32;
     static constexpr int MAIN_DOUBLES = RING_DOUBLES + YBUF_DOUBLES + BRING_DOUBLES;
-    static constexpr int NBAR = 2 * S + 3;
+    static constexpr int NBAR = 1 + 4 + 1;                      // full | yfree[2][2] | yready
     static constexpr size_t SMEM_BYTES = (size_t)MAIN_DOUBLES * 8 + NBAR * 8 + 16;
     static constexpr int OFF_V1 = W * W, OFF_FF = W * W + W, OFF_V2 = W * W + W + 2;
     static constexpr int REC = W * W + 2 * W + 2;
@@ -672,32 +676,38 @@ __device__ __forceinline__ void gram2c_consumer(int role, int64_t njobs, int64_t
                                                 const double* __restrict__ J,
                                                 const double* __restrict__ f,
                                                 const double* __restrict__ rinvp, int n,
-                                                double* smem, uint64_t* full, uint64_t* empty,
-                                                uint64_t* yfree, uint64_t* yready,
-                                                double* __restrict__ rec, uint32_t crank) {
+                                                double* smem, uint64_t* full, uint64_t* yfree,
+                                                uint64_t* yready, double* __restrict__ rec,
+                                                uint32_t crank) {
     typedef Gram2C L;
-    constexpr int NB = L::NB, S = L::S, W = L::W, QR = L::QR, QS = L::QS, RB = L::RB;
+    constexpr int NB = L::NB, W = L::W, QR = L::QR, QS = L::QS, RB = L::RB;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int lr = lane >> 2, lc = lane & 3;
     const int RS = EXACT ? W : n;
-    double* ybuf = smem + L::RING_DOUBLES;
+    double* ybuf0 = smem + L::RING_DOUBLES;
     const double* bring = smem + L::RING_DOUBLES + L::YBUF_DOUBLES + warp * (RB * 2 * 32) + lane;
     const uint32_t bring_s = smem_u32(bring);
     const uint32_t peer = crank ^ 1u;
-    const uint32_t ybuf_peer = map_to_cta(smem_u32(ybuf), peer);
+    const uint32_t ybuf0_peer = map_to_cta(smem_u32(ybuf0), peer);
     const uint32_t yready_peer = map_to_cta(smem_u32(yready), peer);
     const uint32_t yready_self = map_to_cta(smem_u32(yready), crank);
-    const uint32_t yfree0_self = map_to_cta(smem_u32(yfree), crank);
-    const uint32_t yfree1_peer = map_to_cta(smem_u32(yfree + 1), peer);
+    // yfree[2 b]: my readers are done with my Y buffer b; yfree[2 b + 1]: the
+    // peer's readers with theirs (they arrive here remotely)
+    const uint32_t yfree_self = map_to_cta(smem_u32(yfree), crank);
+    const uint32_t yfree_peer = map_to_cta(smem_u32(yfree), peer);
     // this warp's two column blocks of Y
     const int j1 = (int)crank * 8 + warp, j2 = NB - 1 - j1;
     const int kmax = 2 * j2 + 2, k1max = 2 * j1 + 2;
     const bool cta0 = crank == 0;
+    const double* tj = smem;
+    const double* tf = tj + 4 * QS;
 
     double acc[L::BPR][2];
 #pragma unroll
     for (int q = 0; q < L::BPR; q++) { acc[q][0] = 0.0; acc[q][1] = 0.0; }
-    double gv[4] = {0.0, 0.0, 0.0, 0.0}, ff = 0.0;   // Y^T f (CTA 0) or J^T f (CTA 1)
+    // Y^T f of my two column blocks (columns 8 j + 2 lc + {0, 1}, partial over
+    // the rows this lane holds), J^T f of column blocks warp + 8 i (CTA 1), f.f
+    double gy1[2] = {0.0, 0.0}, gy2[2] = {0.0, 0.0}, gj[4] = {0.0, 0.0, 0.0, 0.0}, ff = 0.0;
     // R1^-1 half fragment of block (kc >> 1, j), k-half kc & 1, for this lane
     auto rin = [&](int kc, int j) -> const double* {
         const int kb = kc >> 1;
@@ -705,21 +715,12 @@ __device__ __forceinline__ void gram2c_consumer(int role, int64_t njobs, int64_t
         return rinvp + (size_t)(q * 2 + (kc & 1)) * 32 + lane;
     };
 
-    int stage = 0;
-    uint32_t phase = 0, yphase = 0;
-    uint32_t ephase[2] = {0u, 0u};        // warp 0: completed uses of each ring stage
+    uint32_t phase = 0;                    // of `full` and `yready`: one completion per tile
+    uint32_t fphase[2] = {0u, 0u};         // of the yfree pair of each Y buffer
+    int yb = 0;
     if (warp == 0 && job0 < njobs) gram2c_issue<EXACT>(job0, 0, m, n, J, f, smem, full);
     for (int64_t t = job0; t < njobs; t += jstride) {
-        if (warp == 0 && t + jstride < njobs) {
-            // the other stage is free once all eight warps have left the tile
-            // before this one (its first use needs no wait)
-            const int ns = stage ^ 1;
-            if (t != job0) { mbar_wait(&empty[ns], ephase[ns]); ephase[ns] ^= 1u; }
-            gram2c_issue<EXACT>(t + jstride, ns, m, n, J, f, smem, full);
-        }
-        mbar_wait(&full[stage], phase);
-        const double* tj = smem + (size_t)stage * L::STAGE_DOUBLES;
-        const double* tf = tj + 4 * QS;
+        mbar_wait(full, phase);
         // ---- phase A: my two column blocks of Y for the four strips ----
         double y1[4][2], y2[4][2];
 #pragma unroll
@@ -767,6 +768,16 @@ __device__ __forceinline__ void gram2c_consumer(int role, int64_t njobs, int64_t
             }
         }
         asm volatile("cp.async.wait_group 0;" ::: "memory");
+        // Y^T f from the fragments in registers: y[s] holds row (quarter lr & 3,
+        // 2 s + (lr >> 2)) of the tile
+#pragma unroll
+        for (int s = 0; s < 4; s++) {
+            const double fr = tf[(lr & 3) * QR + 2 * s + (lr >> 2)];
+            gy1[0] = fma(y1[s][0], fr, gy1[0]);
+            gy1[1] = fma(y1[s][1], fr, gy1[1]);
+            gy2[0] = fma(y2[s][0], fr, gy2[0]);
+            gy2[1] = fma(y2[s][1], fr, gy2[1]);
+        }
         if (!cta0) {
             // J^T f of my column blocks straight from the raw tile (trf.py:244)
 #pragma unroll 1
@@ -777,13 +788,19 @@ __device__ __forceinline__ void gram2c_consumer(int role, int64_t njobs, int64_t
                 for (int i = 0; i < 4; i++) {
                     const int b = warp + 8 * i;
                     const double raw = (EXACT || 8 * b + lr < n) ? rawb[8 * b] : 0.0;
-                    gv[i] = fma(raw, fk, gv[i]);
+                    gj[i] = fma(raw, fk, gj[i]);
                 }
             }
+        } else if (warp == 0) {
+            const double fk = tf[lane];                  // T = 32 rows
+            ff = fma(fk, fk, ff);
         }
-        // everyone (both CTAs) is done reading the Y buffers of the last tile
-        mbar_wait_cluster(&yfree[0], yphase ^ 1);
-        mbar_wait_cluster(&yfree[1], yphase ^ 1);
+        // the readers (both CTAs) of the tile that used this Y buffer last are done
+        double* ybuf = ybuf0 + yb * 4 * QS;
+        const uint32_t ybuf_peer = ybuf0_peer + (uint32_t)(yb * 4 * QS) * 8u;
+        mbar_wait_cluster(&yfree[2 * yb], fphase[yb] ^ 1);
+        mbar_wait_cluster(&yfree[2 * yb + 1], fphase[yb] ^ 1);
+        fphase[yb] ^= 1u;
         {
             const int odd = lr & 1;
 #pragma unroll
@@ -811,43 +828,55 @@ __device__ __forceinline__ void gram2c_consumer(int role, int64_t njobs, int64_t
             mbar_arrive_cluster(yready_self);
             mbar_arrive_cluster(yready_peer);
         }
-        mbar_wait_cluster(yready, yphase);
+        mbar_wait_cluster(yready, phase);
+        // all sixteen warps are past phase A: the J stage is free
+        if (warp == 0 && t + jstride < njobs)
+            gram2c_issue<EXACT>(t + jstride, 0, m, n, J, f, smem, full);
         // ---- phase B: my Gram blocks += Y^T Y (block list by role) ----
 #pragma unroll 1
         for (int kc = 0; kc < QR; kc++) {
             const double* base = ybuf + lc * QS + kc * W + lr;
             gram2c_blocks_dispatch(role, acc, base, std::make_integer_sequence<int, L::ROLES>{});
-            if (cta0) {
-                const double fk = tf[lc * QR + kc];
-#pragma unroll
-                for (int i = 0; i < 4; i++) gv[i] = fma(base[8 * (warp + 8 * i)], fk, gv[i]);
-                if (warp == 0 && lr == 0) ff = fma(fk, fk, ff);
-            }
         }
         __syncwarp();
         if (lane == 0) {
-            mbar_arrive(&empty[stage]);
-            mbar_arrive_cluster(yfree0_self);      // my yfree[0]
-            mbar_arrive_cluster(yfree1_peer);      // the peer's yfree[1]
+            mbar_arrive_cluster(yfree_self + (uint32_t)(2 * yb) * 8u);        // my yfree[2 yb]
+            mbar_arrive_cluster(yfree_peer + (uint32_t)(2 * yb + 1) * 8u);    // peer's yfree[2 yb + 1]
         }
-        if (++stage == S) { stage = 0; phase ^= 1; }
-        yphase ^= 1;
+        phase ^= 1u;
+        yb ^= 1;
     }
-    // ---- this CTA's record: its half of the Gram blocks, its vector part ----
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-        gv[i] += __shfl_xor_sync(0xffffffffu, gv[i], 1);
-        gv[i] += __shfl_xor_sync(0xffffffffu, gv[i], 2);
-    }
-    ff += __shfl_xor_sync(0xffffffffu, ff, 1);
-    ff += __shfl_xor_sync(0xffffffffu, ff, 2);
+    // ---- this CTA's record: its half of the Gram blocks, its vector parts ----
     gram2c_store_dispatch(role, acc, rec, lr, lc, std::make_integer_sequence<int, L::ROLES>{});
-    if (lc == 0) {
+    // Y^T f: sum over the rows (lr), lanes lr == 0 hold columns 8 j + 2 lc + {0, 1}
 #pragma unroll
-        for (int i = 0; i < 4; i++)
-            rec[(cta0 ? L::OFF_V1 : L::OFF_V2) + 8 * (warp + 8 * i) + lr] = gv[i];
+    for (int off = 4; off < 32; off <<= 1) {
+        gy1[0] += __shfl_xor_sync(0xffffffffu, gy1[0], off);
+        gy1[1] += __shfl_xor_sync(0xffffffffu, gy1[1], off);
+        gy2[0] += __shfl_xor_sync(0xffffffffu, gy2[0], off);
+        gy2[1] += __shfl_xor_sync(0xffffffffu, gy2[1], off);
     }
-    if (cta0 && warp == 0 && lane == 0) rec[L::OFF_FF] = ff;
+    if (lr == 0) {
+        rec[L::OFF_V1 + 8 * j1 + 2 * lc] = gy1[0];
+        rec[L::OFF_V1 + 8 * j1 + 2 * lc + 1] = gy1[1];
+        rec[L::OFF_V1 + 8 * j2 + 2 * lc] = gy2[0];
+        rec[L::OFF_V1 + 8 * j2 + 2 * lc + 1] = gy2[1];
+    }
+    if (!cta0) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            gj[i] += __shfl_xor_sync(0xffffffffu, gj[i], 1);
+            gj[i] += __shfl_xor_sync(0xffffffffu, gj[i], 2);
+        }
+        if (lc == 0) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) rec[L::OFF_V2 + 8 * (warp + 8 * i) + lr] = gj[i];
+        }
+    } else if (warp == 0) {
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) ff += __shfl_xor_sync(0xffffffffu, ff, off);
+        if (lane == 0) rec[L::OFF_FF] = ff;
+    }
 }
 
 template <bool EXACT>
@@ -855,13 +884,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Gram2C::THREADS, 1)
 gram2c_kernel(int64_t m, int n, const double* __restrict__ J, const double* __restrict__ f,
               const double* __restrict__ rinvp, double* __restrict__ partial) {
     typedef Gram2C L;
-    constexpr int T = L::T, S = L::S, CW = L::CW, W = L::W, QR = L::QR, QS = L::QS;
+    constexpr int T = L::T, CW = L::CW;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* smem = reinterpret_cast<double*>(smem_raw);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + L::MAIN_DOUBLES);
-    uint64_t* empty = full + S;
-    uint64_t* yfree = empty + S;          // [0] mine, [1] the peer's readers
-    uint64_t* yready = yfree + 2;
+    uint64_t* yfree = full + 1;           // [2 b] mine, [2 b + 1] the peer's readers, b = 0, 1
+    uint64_t* yready = yfree + 4;
     const int warp = threadIdx.x >> 5;
     const uint32_t crank = cluster_ctarank();
     double* rec = partial + (size_t)blockIdx.x * L::REC;
@@ -869,12 +897,8 @@ gram2c_kernel(int64_t m, int n, const double* __restrict__ J, const double* __re
     for (int i = threadIdx.x; i < L::MAIN_DOUBLES; i += L::THREADS) smem[i] = 0.0;
     for (int i = threadIdx.x; i < L::REC; i += L::THREADS) rec[i] = 0.0;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < S; s++) {
-            mbar_init(&full[s], 1);
-            mbar_init(&empty[s], CW);
-        }
-        mbar_init(&yfree[0], CW);
-        mbar_init(&yfree[1], CW);
+        mbar_init(full, 1);
+        for (int b = 0; b < 4; b++) mbar_init(&yfree[b], CW);
         mbar_init(yready, 2 * CW);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -885,7 +909,7 @@ gram2c_kernel(int64_t m, int n, const double* __restrict__ J, const double* __re
     const int64_t njobs = (m + T - 1) / T;
     const int64_t job0 = blockIdx.x >> 1, jstride = gridDim.x >> 1;
     gram2c_consumer<EXACT>((int)crank * CW + warp, njobs, job0, jstride, m, J, f, rinvp, n, smem,
-                           full, empty, yfree, yready, rec, crank);
+                           full, yfree, yready, rec, crank);
     // neither CTA may exit while the other can still write into its shared memory
     __syncthreads();
     cluster_sync_all();

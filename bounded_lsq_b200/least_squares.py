@@ -205,7 +205,6 @@ def _least_squares_batched(lib, fun, x0, jac, bounds, method, ftol, xtol, gtol,
                         max_nfev, scaling, diff_step=diff_step, **options)
     res = OptimizeResult(out)
     res.fun = cb.f(res.x, None)
-    res.x_covariance = None
     # per-problem texts: res.message[int(res.status[b])]
     res.message = dict(TERMINATION_MESSAGES)
     res.message[L.STATUS_ERR_TR_ZERO] = "ValueError: `s` is zero."
@@ -299,6 +298,11 @@ def least_squares(fun, x0, jac='2-point', bounds=(-float('inf'), float('inf')),
     ``fun(x, *args, **kwargs)`` receives a 1-D float64 CUDA tensor and returns
     the residuals as a tensor (or scalar); ``jac`` likewise returns (m, n).
     Result fields that are arrays in the reference are CUDA tensors here.
+
+    ``x_covariance`` is None as in the reference ('trf' / 'dogbox' leave it
+    unset, trf.py:261,358); ``options={'x_covariance': True}`` fills it with
+    the field's documented meaning (least_squares.py:248-252: the inverse of
+    J^T J at the solution) from the triangular factor the solve already holds.
     """
     lib = _lib if _lib is not None else L.get_lib()
     _validate_common(method, bounds, jac)
@@ -346,12 +350,16 @@ def _least_squares(lib, fun, x0, jac, bounds, method, ftol, xtol, gtol, max_nfev
                         gtol, max_nfev, scaling, diff_step=diff_step,
                         **options)
     x = out["x"][0]
+    cov = out["x_covariance"]
+    if cov is not None:
+        # "if the inverse doesn't exist this field is set to None"
+        cov = None if bool(torch.isnan(cov[0]).any().item()) else cov[0]
     res = OptimizeResult(
         x=x, fun=fun_b(x.reshape(1, n))[0], obj_value=float(out["obj_value"][0]),
         optimality=float(out["optimality"][0]),
         active_mask=out["active_mask"][0], nfev=int(out["nfev"][0]),
         njev=int(out["njev"][0]), status=int(out["status"][0]),
-        x_covariance=None)
+        x_covariance=cov)
     if callable(jac):
         res.jac = jac_b(x.reshape(1, n))[0]
     else:

@@ -102,6 +102,7 @@ def solve_tall(lib, method, fun, jac, x0, lb, ub, ftol, xtol, gtol, max_nfev,
     group = opts.pop("group", None)
     timers = opts.pop("timers", None)
     trace = opts.pop("trace", None)
+    want_cov = bool(opts.pop("x_covariance", False))
     if opts:
         # trf.py:173 / dogbox.py:100 accept no extra options
         raise TypeError(f"{method}() got an unexpected keyword argument "
@@ -300,10 +301,18 @@ def solve_tall(lib, method, fun, jac, x0, lb, ub, ftol, xtol, gtol, max_nfev,
         ob = lay["on_bound"]
         mask = istate[ob:ob + n].to(torch.int64)
     ist = istate[:4].tolist()
+    cov = None
+    if want_cov and info == 0.0:
+        # (J^T J)^-1 = R^-1 R^-T from the factor at the returned x
+        cov = torch.empty((n, n), dtype=f64, device=dev)
+        lib.call("blsq_covariance", 1, n, fac.data_ptr(), 0, lay["R"], 0,
+                 cov.data_ptr(), st)
+        if bool(torch.isnan(cov).any().item()):
+            cov = None
     res = OptimizeResult(
         x=x, fun=f_cur, jac=J_cur, obj_value=float(state[lay["obj"]].item()),
         optimality=float(state[lay["gnorm"]].item()), active_mask=mask,
-        nfev=ist[1], njev=ist[2], status=ist[0], x_covariance=None)
+        nfev=ist[1], njev=ist[2], status=ist[0], x_covariance=cov)
     res.message = TERMINATION_MESSAGES[res.status]
     res.success = res.status > 0
     res.kernel_launches = launches[0]

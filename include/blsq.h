@@ -79,6 +79,13 @@ int blsq_scaling_vector(int64_t B, int n, const double* x, const double* g,
 /* bounds.py:19-21 in_bounds; ok[b] = 1/0 */
 int blsq_in_bounds(int64_t B, int n, const double* x, const double* lb,
                    const double* ub, int bstride, uint8_t* ok, void* stream);
+/* least_squares.py:248-252 x_covariance = (J^T J)^-1, from the triangular
+ * factor of J kept by the solve: R packed upper (packed = 1; batched state
+ * records: rec = state, stride = record size, r_off = layout R) or dense
+ * row-major n x n (packed = 0; tall mode: rec = fac + R).  cov (B, n, n);
+ * NaN where R is singular ("the inverse doesn't exist"). */
+int blsq_covariance(int64_t B, int n, const double* rec, int64_t stride, int r_off,
+                    int packed, double* cov, void* stream);
 /* dogbox.py:9-35 find_intersection; flags bit0 orig_l, bit1 orig_u,
  * bit2 tr_l, bit3 tr_u */
 int blsq_find_intersection(int64_t B, int n, const double* x, const double* tr,

@@ -1151,3 +1151,44 @@ def check_tall_edge_cases_vs_oracle(lib, dev):
                 assert res.status >= 0, (kappa, s)
                 assert res.obj_value <= r.obj_value * 1.01, (kappa, s)
     return out
+
+
+def check_x_covariance(lib, dev):
+    """options={'x_covariance': True}: (J^T J)^-1 at the solution (the meaning
+    least_squares.py:248-252 documents) from the factor the solve holds,
+    batched / single / tall; the default stays None as in the reference
+    (trf.py:261,358)."""
+    from bounded_lsq_b200.synthetic import TallLinExp
+    model = ExpDecay2()
+    B = 16
+    _, y = model.make_data(B, seed=1)
+    for method in ("trf", "dogbox"):
+        r = least_squares_batched(model.fun_t, T(np.tile(model.x0, (B, 1)), dev),
+                                  jac=model.jac_t, bounds=(model.lb, model.ub),
+                                  method=method, args=(PerProblem(T(y, dev)),),
+                                  options=dict(x_covariance=True), _lib=lib)
+        X = r.x.cpu().numpy()
+        C = r.x_covariance.cpu().numpy()
+        for b in range(B):
+            J = model.jac_np(X[b])
+            if np.linalg.cond(J) > 1e4:
+                continue                  # inv(J^T J) itself is not defined to 1e-7
+            Rq = np.linalg.qr(J, mode="r")
+            Ti = np.linalg.inv(Rq)
+            ref = Ti @ Ti.T
+            assert np.abs(C[b] - ref).max() <= 1e-8 * np.abs(ref).max(), (method, b)
+    wl = TallLinExp(3000, 12, seed=1, x0_tail=(0.8, 1.5, 0.3, 4.0)).to_device(dev)
+    rr = least_squares(wl.fun_t, T(wl.x0, dev), jac=wl.jac_t,
+                       bounds=(T(wl.lb, dev), T(wl.ub, dev)),
+                       options=dict(x_covariance=True), _lib=lib)
+    J = wl.jac_np(rr.x.cpu().numpy())
+    ref = np.linalg.inv(J.T @ J)
+    assert np.abs(rr.x_covariance.cpu().numpy() - ref).max() <= 1e-8 * np.abs(ref).max()
+    r1 = least_squares(lambda x: x - 1.0, T([3.0], dev), options=dict(x_covariance=True), _lib=lib)
+    assert r1.x_covariance.shape == (1, 1) and float(r1.x_covariance[0, 0]) == 1.0
+    assert least_squares(lambda x: x - 1.0, T([3.0], dev), _lib=lib).x_covariance is None
+    # singular J^T J ("the inverse doesn't exist") -> None
+    A = T(np.array([[1.0, 1.0], [2.0, 2.0], [3.0, 3.0]]), dev)
+    r2 = least_squares(lambda x: A @ x - 1.0, T([0.0, 0.0], dev), jac=lambda x: A,
+                       options=dict(x_covariance=True), _lib=lib)
+    assert r2.x_covariance is None

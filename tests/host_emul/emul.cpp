@@ -324,6 +324,39 @@ int blsq_round_batched(int method, int64_t A, const int32_t* idx, int m, int n,
     return 0;
 }
 
+int blsq_covariance(int64_t B, int n, const double* rec, int64_t stride, int r_off,
+                    int packed, double* cov, void*) {
+    for (int64_t b = 0; b < B; b++) {
+        const double* R = rec + b * stride + r_off;
+        double* C = cov + b * (int64_t)n * n;
+        auto r = [&](int i, int j) {
+            return packed ? R[i * n - (i * (i - 1)) / 2 + (j - i)] : R[(int64_t)i * n + j];
+        };
+        bool singular = false;
+        for (int i = 0; i < n; i++) singular = singular || !(r(i, i) != 0.0);
+        if (singular) {
+            for (int e = 0; e < n * n; e++) C[e] = std::nan("");
+            continue;
+        }
+        std::vector<double> T((size_t)n * n, 0.0);
+        for (int j = 0; j < n; j++)
+            for (int i = j; i >= 0; i--) {
+                if (i == j) { T[(size_t)i * n + j] = 1.0 / r(i, i); continue; }
+                double acc = 0.0;
+                for (int k = i + 1; k <= j; k++) acc = fma(r(i, k), T[(size_t)k * n + j], acc);
+                T[(size_t)i * n + j] = -acc / r(i, i);
+            }
+        for (int i = 0; i < n; i++)
+            for (int j = 0; j < n; j++) {
+                double acc = 0.0;
+                for (int k = (i > j ? i : j); k < n; k++)
+                    acc = fma(T[(size_t)i * n + k], T[(size_t)j * n + k], acc);
+                C[(int64_t)i * n + j] = acc;
+            }
+    }
+    return 0;
+}
+
 int blsq_dogbox_on_bound(int64_t B, int n, const int32_t* istate,
                          int64_t* mask, void*) {
     for (int64_t b = 0; b < B; b++)

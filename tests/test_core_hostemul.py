@@ -100,6 +100,10 @@ def test_benchmark_table(lib, tmp_path):
     assert st["instances"] == 58 and st["checked"] >= 130
 
 
+def test_x_covariance(lib):
+    cases.check_x_covariance(lib, DEV)
+
+
 def test_compact_batched(lib):
     cases.check_compact_batched(lib, DEV)
 

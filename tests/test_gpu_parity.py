@@ -242,6 +242,10 @@ def test_benchmark_table(lib, dev, tmp_path):
     assert st["instances"] == 58 and st["checked"] >= 130
 
 
+def test_x_covariance(lib, dev):
+    cases.check_x_covariance(lib, dev)
+
+
 def test_compact_batched(lib, dev):
     cases.check_compact_batched(lib, dev)
 

@@ -14,7 +14,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv,noheader > gpur
 for step in "$@"; do
   name=${step%%=*}; arg=""; [[ "$step" == *=* ]] && arg=${step#*=}
   case $name in
-    tests) python -m pytest tests -m gpu -x -q $arg > gpurun_out/${TAG}_pytest.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/${TAG}_pytest.log; tail -15 gpurun_out/${TAG}_pytest.log;;
+    tests) python -m pytest tests -m gpu -x -q ${arg:+-k "$arg"} > gpurun_out/${TAG}_pytest.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/${TAG}_pytest.log; tail -15 gpurun_out/${TAG}_pytest.log;;
     smoke) python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${TAG}_smoke.log 2>&1; echo "smoke rc=$?"; tail -5 gpurun_out/${TAG}_smoke.log;;
     bench) k=$(echo "$arg" | tr -c 'a-zA-Z0-9' '_'); python bench.py $arg > gpurun_out/${TAG}_bench_${k}.json 2> gpurun_out/${TAG}_bench_${k}.err; echo "bench $arg rc=$?"; tail -c 1500 gpurun_out/${TAG}_bench_${k}.json; tail -5 gpurun_out/${TAG}_bench_${k}.err;;
     launches) ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file gpurun_out/${TAG}_launches_${arg}.csv python bench.py --workload $arg --steps 1 --warmup 1 --no-cpu-baseline --no-tall > gpurun_out/${TAG}_launches_${arg}.log 2>&1; echo "launches rc=$?";;
