@@ -241,8 +241,12 @@ __global__ void covariance_kernel(int64_t B, int n, const double* __restrict__ r
     auto r = [&](int i, int j) -> double {
         return packed ? R[i * n - (i * (i - 1)) / 2 + (j - i)] : R[(int64_t)i * n + j];
     };
+    // pivots at rounding level of the largest one: J^T J has no inverse
+    double dmax = 0.0;
+    for (int i = 0; i < n; i++) dmax = fabs(r(i, i)) > dmax ? fabs(r(i, i)) : dmax;
     bool singular = false;
-    for (int i = 0; i < n; i++) singular = singular || !(r(i, i) != 0.0);
+    for (int i = 0; i < n; i++)
+        singular = singular || !(fabs(r(i, i)) > 16.0 * n * 2.220446049250313e-16 * dmax);
     if (singular) {
         for (int e = 0; e < n * n; e++) C[e] = nan("");
         return;

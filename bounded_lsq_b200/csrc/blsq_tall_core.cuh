@@ -557,32 +557,18 @@ BLSQ_HD bool tall_gn_try(const Blk& B, const double* A, const TallWork& W, doubl
     return tall_tri_try(B, A, W, W.n, nullptr, EPS * m, pgn, pnorm);
 }
 
-// dogbox.py:197, newton_step = lstsq(J_free, -f)[0], without singular values:
-// Householder QR of the free columns of R (a staircase: column fl[c] has
-// entries down to row fl[c] only), the same reflectors on Q^T f, then the
-// certified triangular solve of tall_tri_try against numpy's
-// rcond = eps * max(m, n_free).  One thread per trailing column (coalesced
-// along the rows of A), ~3 block barriers per column.  Returns false when the
-// certificate fails (the caller then takes the SVD route, which rebuilds A).
-BLSQ_HD bool tall_dogbox_ls(const Blk& B, const double* R, const TallWork& W, double* A,
-                            int nfree, double m, double* newton, double* pnorm_slot) {
+// Householder QR of a column staircase of A (n x n, row major): position p is
+// matrix column cols[p], whose entries reach down to row ext[p] >= p.  The
+// reflectors are also applied to the trailing staircase columns, to the nx
+// extra columns cols[nc .. nc + nx) (all rows) and to W.b.  One thread per
+// trailing column (coalesced along the rows of A), ~3 block barriers per column.
+BLSQ_HD void tall_staircase_qr(const Blk& B, double* A, const TallWork& W, const int* cols,
+                               const int* ext, int nc, int nx) {
     const int n = W.n;
-    int* fl = W.hits;                                 // free columns, ascending
-    for (int e = B.tid; e < n * n; e += B.nt) {
-        const int i = e / n, j = e % n;
-        A[e] = (j >= i && W.fr[j]) ? R[e] : 0.0;
-    }
-    for (int i = B.tid; i < n; i += B.nt) W.b[i] = W.qtf[i];
-    if (B.tid == 0) {
-        int c = 0;
-        for (int j = 0; j < n; j++)
-            if (W.fr[j]) fl[c++] = j;
-    }
-    B.sync();
     double* v = W.w;
-    for (int c = 0; c < nfree; c++) {
-        const int jc = fl[c];
-        const int len = jc - c + 1;                   // rows c .. jc
+    for (int c = 0; c < nc; c++) {
+        const int jc = cols[c];
+        const int len = ext[c] - c + 1;               // rows c .. ext[c]
         if (len <= 1) continue;                       // already triangular here
         double nn = 0.0;
         for (int r = B.tid; r < len; r += B.nt) {
@@ -601,11 +587,11 @@ BLSQ_HD bool tall_dogbox_ls(const Blk& B, const double* R, const TallWork& W, do
         B.sync();
         if (B.tid == 0) v[0] = u0;
         B.sync();
-        // trailing free columns and the right-hand side (index nfree)
-        for (int cc = c + 1 + B.tid; cc <= nfree; cc += B.nt) {
+        // trailing columns, extra columns and the right-hand side (index nc + nx)
+        for (int cc = c + 1 + B.tid; cc <= nc + nx; cc += B.nt) {
             double w = 0.0;
-            if (cc < nfree) {
-                const int j = fl[cc];
+            if (cc < nc + nx) {
+                const int j = cols[cc];
                 for (int r = 0; r < len; r++) w = fma(v[r], A[(size_t)(c + r) * n + j], w);
                 w *= beta;
                 for (int r = 0; r < len; r++)
@@ -619,9 +605,201 @@ BLSQ_HD bool tall_dogbox_ls(const Blk& B, const double* R, const TallWork& W, do
         if (B.tid == 0) A[(size_t)c * n + jc] = alpha;
         B.sync();
     }
+}
+
+// Minimum-norm least squares for a NUMERICALLY RANK-DEFICIENT triangle (the
+// C4 / C5 benchmark start: two pairs of identical columns, and dogbox never
+// breaks the symmetry, so every iterate is rank deficient) without singular
+// values.  In: A holds the QR factor T of the free columns (positions 0..nfree,
+// matrix columns fl[.]) from tall_dogbox_ls, W.b the rotated right-hand side.
+//   1. D = positions whose diagonal collapsed (|T_dd| <= 1e-10 max |T_ii|; at
+//      most KMAX of them), I = the others.  The columns of D go to the end:
+//      [T_I | T_D] is a staircase again (steps of at most |D| rows), one more
+//      pass of short reflectors gives  [R11 R12; 0 R22].
+//   2. Accept only when the rank decision is unambiguous against numpy's
+//      rcond = eps max(m, n_free) (dogbox.py:197 -> gelsd): R11 certified well
+//      above the cut (tall_tri_try with a 100x margin), |R22|_F at least 100x
+//      below it, |W|_F^2 <= 100 for W = R11^-1 R12.  Otherwise: false, and the
+//      caller takes the SVD.
+//   3. z_I = -R11^-1 c1 is a particular solution, N = [-W; I] spans the null
+//      space; the minimum-norm solution is z - N (N^T N)^-1 N^T z:
+//        y = (I + W^T W)^-1 W^T z_I,   z_I <- z_I - W y,   z_D = y.
+// For an exact duplicate W = e_i and the step is split evenly, as gelsd does.
+BLSQ_HD bool tall_dogbox_ls_deficient(const Blk& B, const TallWork& W, double* A, int nfree,
+                                      double m, double* newton, double* pnorm_slot) {
+    constexpr int KMAX = 8;
+    const int n = W.n;
+    // scratch for the K x K system: x_edge | refl | c_h are consecutive vectors
+    // (TallWork::carve) and unused at this point of the propose: 3 n doubles
+    int kcap = KMAX;
+    while (kcap * kcap > 3 * n) kcap--;
+    double* scr = W.x_edge;
+    const int* fl = W.hits;               // free columns by position
+    int* cols = W.flags;                  // I positions first, then D
+    int* ext = W.marks;
+    double dmax = 0.0;
+    for (int c = B.tid; c < nfree; c += B.nt) {
+        const double a = fabs(A[(size_t)c * n + fl[c]]);
+        if (a > dmax) dmax = a;
+    }
+    dmax = blk_max(B, dmax);
+    if (!(dmax > 0.0)) return false;
+    B.sync();
+    if (B.tid == 0) {
+        int ni = 0, nd = 0;
+        for (int c = 0; c < nfree; c++)
+            if (fabs(A[(size_t)c * n + fl[c]]) <= 1e-10 * dmax) nd++;
+        int pi = 0, pd = nfree - nd;
+        if (nd >= 1 && nd <= kcap) {
+            for (int c = 0; c < nfree; c++) {
+                const bool dep = fabs(A[(size_t)c * n + fl[c]]) <= 1e-10 * dmax;
+                const int p = dep ? pd++ : pi++;
+                cols[p] = fl[c];
+                ext[p] = c;               // T is upper triangular: rows 0 .. c
+            }
+        }
+        ni = nfree - nd;
+        B.ired[0] = nd;
+        B.ired[1] = ni;
+    }
+    B.sync();
+    const int nd = B.ired[0], r = B.ired[1];
+    B.sync();
+    if (nd < 1 || nd > kcap || r < 1) return false;
+    // the dependent columns hold stale reflector data under their diagonal
+    for (int e = 0; e < nd; e++) {
+        const int j = cols[r + e], d = ext[r + e];
+        for (int i = d + 1 + B.tid; i < nfree; i += B.nt) A[(size_t)i * n + j] = 0.0;
+    }
+    B.sync();
+    tall_staircase_qr(B, A, W, cols, ext, r, nd);
+    // |R22|_F and |T|_F (an upper bound of s_max; s_max >= |T|_F / sqrt(nfree))
+    double r22 = 0.0, tf2 = 0.0;
+    for (int e = B.tid; e < nfree * nfree; e += B.nt) {
+        const int i = e / nfree, p = e % nfree;
+        if (p < r && i > p) continue;
+        const double a = A[(size_t)i * n + cols[p]];
+        tf2 = fma(a, a, tf2);
+        if (p >= r && i >= r) r22 = fma(a, a, r22);
+    }
+    double z0 = 0.0;
+    blk_sum3(B, r22, tf2, z0);
+    const double mx = m > nfree ? m : (double)nfree;
+    const double cut_lo = EPS * mx * sqrt(tf2 / nfree);
+    if (!(sqrt(r22) < 0.01 * cut_lo)) return false;
+    double* sol = W.suf;
+    if (!tall_tri_try(B, A, W, r, cols, 100.0 * EPS * mx, sol, pnorm_slot)) return false;
+    // W = R11^-1 R12, one warp per dependent column, in place
+    double* t = W.rowbuf + (size_t)B.warp * n;
+    for (int e = B.warp; e < nd; e += B.nwarps) {
+        const int je = cols[r + e];
+        for (int i = r - 1; i >= 0; i--) {
+            const double* ai = A + (size_t)i * n;
+            double acc = 0.0;
+            for (int k = i + 1 + B.lane; k < r; k += B.lanes) acc = fma(ai[cols[k]], t[k], acc);
+            acc = warp_sum(acc);
+            const double ti = (ai[je] - acc) / ai[cols[i]];
+            if (B.lane == 0) t[i] = ti;
+#if BLSQ_TALL_DEV
+            __syncwarp();
+#endif
+        }
+        for (int i = B.lane; i < r; i += B.lanes) A[(size_t)i * n + je] = t[i];
+    }
+    B.sync();
+    // M = I + W^T W, h = W^T z_I
+    double* Mh = W.tv;                    // y (K doubles)
+    double* hv = W.t3;                    // W^T z_I (K doubles)
+    double wf = 0.0;
+    for (int a1 = 0; a1 < nd; a1++) {
+        for (int a2 = a1; a2 <= nd; a2++) {
+            double acc = 0.0;
+            for (int i = B.tid; i < r; i += B.nt) {
+                const double wa = A[(size_t)i * n + cols[r + a1]];
+                acc = fma(wa, a2 < nd ? A[(size_t)i * n + cols[r + a2]] : sol[i], acc);
+            }
+            acc = blk_sum(B, acc);
+            if (B.tid == 0) {
+                if (a2 < nd) scr[a1 * kcap + a2] = acc;
+                else hv[a1] = acc;
+            }
+            if (a2 == a1) wf += acc;
+        }
+    }
+    B.sync();
+    if (!(wf <= 100.0)) return false;
+    if (B.tid == 0) {
+        // Cholesky of the K x K matrix I + W^T W, then y
+        double Mm[KMAX][KMAX], y[KMAX];
+        for (int a1 = 0; a1 < nd; a1++)
+            for (int a2 = 0; a2 < nd; a2++)
+                Mm[a1][a2] = (a1 <= a2 ? scr[a1 * kcap + a2] : scr[a2 * kcap + a1]) +
+                             (a1 == a2 ? 1.0 : 0.0);
+        for (int k = 0; k < nd; k++) {
+            Mm[k][k] = sqrt(Mm[k][k]);
+            for (int i = k + 1; i < nd; i++) Mm[i][k] /= Mm[k][k];
+            for (int j = k + 1; j < nd; j++)
+                for (int i = j; i < nd; i++) Mm[i][j] -= Mm[i][k] * Mm[j][k];
+        }
+        for (int i = 0; i < nd; i++) {
+            double sacc = hv[i];
+            for (int k = 0; k < i; k++) sacc -= Mm[i][k] * y[k];
+            y[i] = sacc / Mm[i][i];
+        }
+        for (int i = nd - 1; i >= 0; i--) {
+            double sacc = y[i];
+            for (int k = i + 1; k < nd; k++) sacc -= Mm[k][i] * y[k];
+            y[i] = sacc / Mm[i][i];
+        }
+        for (int i = 0; i < nd; i++) Mh[i] = y[i];
+    }
+    B.sync();
+    for (int i = B.tid; i < n; i += B.nt) newton[i] = 0.0;
+    B.sync();
+    double nn = 0.0;
+    for (int i = B.tid; i < r; i += B.nt) {
+        double zi = sol[i];
+        for (int e = 0; e < nd; e++) zi = fma(-A[(size_t)i * n + cols[r + e]], Mh[e], zi);
+        newton[cols[i]] = zi;
+        nn = fma(zi, zi, nn);
+    }
+    for (int e = B.tid; e < nd; e += B.nt) {
+        newton[cols[r + e]] = Mh[e];
+        nn = fma(Mh[e], Mh[e], nn);
+    }
+    nn = blk_sum(B, nn);
+    if (B.tid == 0) *pnorm_slot = sqrt(nn);
+    B.sync();
+    return true;
+}
+
+// dogbox.py:197, newton_step = lstsq(J_free, -f)[0], without singular values:
+// Householder QR of the free columns of R (a staircase: column fl[c] has
+// entries down to row fl[c] only), the same reflectors on Q^T f, then the
+// certified triangular solve of tall_tri_try against numpy's
+// rcond = eps * max(m, n_free); a triangle whose diagonal has collapsed goes
+// through tall_dogbox_ls_deficient.  Returns false when neither applies (the
+// caller then takes the SVD route, which rebuilds A).
+BLSQ_HD bool tall_dogbox_ls(const Blk& B, const double* R, const TallWork& W, double* A,
+                            int nfree, double m, double* newton, double* pnorm_slot) {
+    const int n = W.n;
+    int* fl = W.hits;                                 // free columns, ascending
+    for (int e = B.tid; e < n * n; e += B.nt) {
+        const int i = e / n, j = e % n;
+        A[e] = (j >= i && W.fr[j]) ? R[e] : 0.0;
+    }
+    for (int i = B.tid; i < n; i += B.nt) W.b[i] = W.qtf[i];
+    if (B.tid == 0) {
+        int c = 0;
+        for (int j = 0; j < n; j++)
+            if (W.fr[j]) fl[c++] = j;
+    }
+    B.sync();
+    tall_staircase_qr(B, A, W, fl, fl, nfree, 0);
     const double mx = m > nfree ? m : (double)nfree;
     double* sol = W.suf;
-    if (!tall_tri_try(B, A, W, nfree, fl, EPS * mx, sol, pnorm_slot)) return false;
+    if (!tall_tri_try(B, A, W, nfree, fl, EPS * mx, sol, pnorm_slot))
+        return tall_dogbox_ls_deficient(B, W, A, nfree, m, newton, pnorm_slot);
     for (int i = B.tid; i < n; i += B.nt) newton[i] = 0.0;
     B.sync();
     for (int c = B.tid; c < nfree; c += B.nt) newton[fl[c]] = sol[c];

@@ -332,8 +332,12 @@ int blsq_covariance(int64_t B, int n, const double* rec, int64_t stride, int r_o
         auto r = [&](int i, int j) {
             return packed ? R[i * n - (i * (i - 1)) / 2 + (j - i)] : R[(int64_t)i * n + j];
         };
+        // pivots at rounding level of the largest one: J^T J has no inverse
+        double dmax = 0.0;
+        for (int i = 0; i < n; i++) dmax = fabs(r(i, i)) > dmax ? fabs(r(i, i)) : dmax;
         bool singular = false;
-        for (int i = 0; i < n; i++) singular = singular || !(r(i, i) != 0.0);
+        for (int i = 0; i < n; i++)
+            singular = singular || !(fabs(r(i, i)) > 16.0 * n * 2.220446049250313e-16 * dmax);
         if (singular) {
             for (int e = 0; e < n * n; e++) C[e] = std::nan("");
             continue;
