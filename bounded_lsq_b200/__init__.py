@@ -5,10 +5,10 @@ path: ``least_squares``, ``trf``, ``dogbox`` and the bound helpers, plus the
 batched entry point ``least_squares_batched``.
 """
 from .least_squares import (least_squares, least_squares_batched, trf, dogbox,
-                            OptimizeResult, TERMINATION_MESSAGES)
+                            stage_host_inputs, OptimizeResult, TERMINATION_MESSAGES)
 from .batched import PerProblem
 from ._lib import BlsqError, get_lib
 
-__all__ = ["least_squares", "least_squares_batched", "trf", "dogbox",
+__all__ = ["least_squares", "least_squares_batched", "trf", "dogbox", "stage_host_inputs",
            "PerProblem", "OptimizeResult", "TERMINATION_MESSAGES",
            "BlsqError", "get_lib"]

@@ -139,7 +139,7 @@ def _as_f64(t, like, what):
 
 
 def solve_batched(lib, method, fun, jac, X0, lb, ub, ftol, xtol, gtol,
-                  max_nfev, scaling, diff_step=None, check_every=1,
+                  max_nfev, scaling, diff_step=None, check_every=2,
                   compact_below=0.75, tail_below=8192, trace=None,
                   timers=None, graph_tail_rounds=None, prologue=None,
                   prologue_rounds=6, x_covariance=False):
@@ -418,8 +418,11 @@ def solve_batched(lib, method, fun, jac, X0, lb, ub, ftol, xtol, gtol,
         rounds += 1
         if trace is not None:
             trace(rounds, idx, Xnew[:A], state, istate)
-        # host look at the status flags: every round while the rounds are
-        # bandwidth-sized, every 4th once they are launch-latency sized
+        # host look at the status flags: every second round while the rounds
+        # are bandwidth-sized (measured 21.3 -> 20.5 ms per C2 solve against
+        # every round; finished problems are skipped inside the kernels, so a
+        # late look only delays a compaction), every 4th once they are
+        # launch-latency sized
         every = check_every if A > tail_below else max(check_every, 4)
         if rounds % every == 0 or rounds >= max_nfev:
             if not fused_count:

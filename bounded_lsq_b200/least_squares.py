@@ -177,6 +177,9 @@ def _least_squares_batched(lib, fun, x0, jac, bounds, method, ftol, xtol, gtol,
     else:
         options.pop("h2d_chunks", None)
         options.pop("device", None)
+    ev0 = getattr(options.get("prologue"), "x0_event", None)
+    if ev0 is not None:                      # staged inputs: x0 is on the copy stream
+        torch.cuda.current_stream(x0.device).wait_event(ev0)
     x0 = x0.to(torch.float64).contiguous()
     if x0.dim() != 2:
         raise ValueError("batched `x0` must be (B, n).")
@@ -217,48 +220,78 @@ def _least_squares_batched(lib, fun, x0, jac, bounds, method, ftol, xtol, gtol,
 _COPY_STREAM = {}
 
 
-def _stage_host_inputs(x0, args, kwargs, options):
-    """Device copies of host-resident batched inputs.  x0 (small) is copied at
-    once; every CPU ``PerProblem`` tensor is copied in ``h2d_chunks`` chunks
-    of problems on a side stream, one event per chunk.  Returns the device x0,
-    the rewritten args/kwargs and the [(c0, c1, event)] plan for
-    ``solve_batched(prologue=...)`` (None if there is nothing to stream)."""
-    dev = options.pop("device", None) or _default_device()
-    dev = torch.device(dev)
-    nch = int(options.pop("h2d_chunks", 4))
+class _StagePlan(list):
+    """[(c0, c1, event)] chunks of a staged batch + the event of the x0 copy."""
+    x0_event = None
+
+
+def stage_host_inputs(x0, args=(), kwargs=None, device=None, h2d_chunks=4, out=None):
+    """Start the host-to-device copies of a batched problem's inputs and return
+    at once: ``(x0_dev, args_dev, kwargs_dev, plan)``.
+
+    x0 (small) and every CPU ``PerProblem`` tensor (ideally pinned) are copied
+    on a side stream, the per-problem data in ``h2d_chunks`` chunks of problems
+    with one event per chunk.  Hand the results to ``least_squares_batched(fun,
+    x0_dev, args=args_dev, kwargs=kwargs_dev, options={'prologue': plan})``:
+    each chunk then runs its first rounds while the next one is still on the
+    wire.  ``least_squares_batched`` does exactly this itself when it is called
+    with CPU tensors; calling it directly lets a serving loop start the copies
+    of the NEXT batch while the current one is being solved.
+
+    out : optional ``(x0_buffer, {id(host tensor): device buffer})`` of
+    preallocated device tensors that are not in use (a double-buffering
+    caller's second set); without it fresh buffers are allocated and the copy
+    stream first waits for the work queued on the current stream.
+    """
+    dev = torch.device(device) if device is not None else _default_device()
+    kwargs = dict(kwargs or {})
     B = x0.shape[0]
-    x0d = x0.to(dev, non_blocking=True)
-    host = [v for v in list(args) + list(dict(kwargs).values())
+    host = [v for v in list(args) + list(kwargs.values())
             if isinstance(v, PerProblem) and not v.tensor.is_cuda]
-    if not host:
-        return x0d, args, kwargs, None
     for v in host:
         if v.tensor.shape[0] != B:
             raise ValueError("PerProblem data must have leading dimension B.")
-    nch = max(1, min(nch, B // 65536))
+    nch = max(1, min(int(h2d_chunks), B // 65536))
     step = -(-B // nch)
-    main = torch.cuda.current_stream(dev)
-    copy = _COPY_STREAM.get(dev)
-    if copy is None:
-        copy = _COPY_STREAM[dev] = torch.cuda.Stream(dev)
-    bufs = {id(v): torch.empty(v.tensor.shape, dtype=v.tensor.dtype, device=dev)
-            for v in host}
-    copy.wait_stream(main)                  # the buffers were allocated on main
-    plan = []
-    with torch.cuda.stream(copy):
-        for c0 in range(0, B, step):
-            c1 = min(B, c0 + step)
-            for v in host:
-                bufs[id(v)][c0:c1].copy_(v.tensor[c0:c1], non_blocking=True)
-            ev = torch.cuda.Event()
-            ev.record(copy)
-            plan.append((c0, c1, ev))
+    with torch.cuda.device(dev):
+        main = torch.cuda.current_stream(dev)
+        copy = _COPY_STREAM.get(dev)
+        if copy is None:
+            copy = _COPY_STREAM[dev] = torch.cuda.Stream(dev)
+        if out is None:
+            x0d = torch.empty(x0.shape, dtype=x0.dtype, device=dev)
+            bufs = {id(v): torch.empty(v.tensor.shape, dtype=v.tensor.dtype, device=dev)
+                    for v in host}
+            copy.wait_stream(main)          # the buffers were allocated on main
+        else:
+            x0d, given = out
+            bufs = {id(v): given[id(v.tensor)] for v in host}
+        plan = _StagePlan()
+        with torch.cuda.stream(copy):
+            x0d.copy_(x0, non_blocking=True)
+            plan.x0_event = torch.cuda.Event()
+            plan.x0_event.record(copy)
+            for c0 in range(0, B, step):
+                c1 = min(B, c0 + step)
+                for v in host:
+                    bufs[id(v)][c0:c1].copy_(v.tensor[c0:c1], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy)
+                plan.append((c0, c1, ev))
 
     def swap(v):
         return PerProblem(bufs[id(v)]) if id(v) in bufs else v
-    args = tuple(swap(v) for v in args)
-    kwargs = {k: swap(v) for k, v in dict(kwargs).items()}
-    return x0d, args, kwargs, plan
+    return (x0d, tuple(swap(v) for v in args), {k: swap(v) for k, v in kwargs.items()},
+            plan)
+
+
+def _stage_host_inputs(x0, args, kwargs, options):
+    """least_squares_batched called with CPU tensors: stage them (see
+    stage_host_inputs).  Returns the device x0, the rewritten args / kwargs and
+    the [(c0, c1, event)] plan for ``solve_batched(prologue=...)``."""
+    dev = options.pop("device", None) or _default_device()
+    nch = int(options.pop("h2d_chunks", 4))
+    return stage_host_inputs(x0, args, kwargs, device=dev, h2d_chunks=nch)
 
 
 def _single_callbacks(fun, jac, args, kwargs, dev):
