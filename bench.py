@@ -42,8 +42,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 # NCCL prints its version banner on stdout at NCCL_DEBUG=VERSION; this script's
 # stdout is ONE JSON line
-if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-    os.environ["NCCL_DEBUG"] = "WARN"
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"      # (also overrides an /etc/nccl.conf setting)
 
 WORKLOADS = {
     # BASELINE.json configs[1]
