@@ -97,6 +97,21 @@ def _side_stream(dev):
     return s
 
 
+_CSTREAM = {}
+
+
+def _count_stream(dev):
+    """Side stream, pinned landing buffer and events of the look-ahead status
+    polls (4-byte copies), one set per device."""
+    s = _CSTREAM.get(dev)
+    if s is None:
+        s = _CSTREAM[dev] = (torch.cuda.Stream(dev),
+                             torch.zeros(2, dtype=torch.int32).pin_memory(),
+                             [torch.cuda.Event(), torch.cuda.Event()],
+                             [torch.cuda.Event(), torch.cuda.Event()])
+    return s
+
+
 _POOL = {}
 
 
@@ -142,7 +157,7 @@ def solve_batched(lib, method, fun, jac, X0, lb, ub, ftol, xtol, gtol,
                   max_nfev, scaling, diff_step=None, check_every=2,
                   compact_below=0.75, tail_below=8192, trace=None,
                   timers=None, graph_tail_rounds=None, prologue=None,
-                  prologue_rounds=6, x_covariance=False):
+                  prologue_rounds=6, x_covariance=False, lookahead=None):
     """Run ``method`` ('trf' | 'dogbox') on B problems.
 
     fun(X, idx) -> (A, m); jac is a callable jac(X, idx) -> (A, m, n) or the
@@ -412,17 +427,104 @@ def solve_batched(lib, method, fun, jac, X0, lb, ub, ftol, xtol, gtol,
                           count_here=False)
         first = 0
         rounds = K
-    while A > 0:
+    def compact(A, idx32, nrun_hint):
+        """Ordered compaction on the device (3 small launches) into the other
+        half of a ping-pong pair; returns the exact number of survivors (one
+        blocking read: compactions are ~10 per solve)."""
+        nonlocal pong, flip, cwork, launches, Xnew, Xjac
+        if pong is None:
+            pong = [dict(X=torch.empty_like(Xnew),
+                         J=None if Xjac is None else torch.empty_like(Xjac),
+                         i32=torch.empty(A, dtype=torch.int32, device=dev),
+                         i64=torch.empty(A, dtype=torch.int64, device=dev)),
+                    dict(X=Xnew, J=Xjac,
+                         i32=torch.empty(A, dtype=torch.int32, device=dev),
+                         i64=torch.empty(A, dtype=torch.int64, device=dev))]
+            cwork = torch.empty(int(lib._dll.blsq_compact_work_size(A)),
+                                dtype=torch.int32, device=dev)
+        o = pong[flip]
+        flip ^= 1
+        lib.call("blsq_compact_batched", A,
+                 None if idx32 is None else idx32.data_ptr(),
+                 istate.data_ptr(), n, Xnew.data_ptr(),
+                 None if Xjac is None else Xjac.data_ptr(),
+                 o["i32"].data_ptr(), o["i64"].data_ptr(),
+                 o["X"].data_ptr(),
+                 None if Xjac is None else o["J"].data_ptr(),
+                 cwork.data_ptr(), lib.stream(X0))
+        launches += 3
+        Xnew, Xjac = o["X"], o["J"]
+        if nrun_hint is None:
+            ntot = int(cwork[int(lib._dll.blsq_compact_work_size(A)) - 1].item())
+        else:
+            ntot = nrun_hint
+        return ntot, o["i64"][:ntot], o["i32"][:ntot]
+
+    # Look-ahead polling (CUDA): round r + 1 is queued BEFORE the host waits for
+    # the running count of round r (copied to pinned memory on a side stream),
+    # so the GPU never idles on a host look; the count that triggers a
+    # compaction is one round old, the compaction itself reports the exact
+    # number of survivors.  The synchronous form is kept for the trace hook,
+    # for BLSQ_ROUND_COUNT=0 and for the host emulation of the tests.
+    # Measured on one B200 the look-ahead form is 0.7 ms per C2 solve SLOWER than
+    # a blocking look every second round (19.5 ms): the GPU is never idle there
+    # anyway and every compaction comes one round later.  It is meant for many
+    # driver processes on one host (8 GPUs), hence opt-in (option `lookahead`
+    # or BLSQ_LOOKAHEAD=1).
+    if lookahead is None:
+        lookahead = os.environ.get("BLSQ_LOOKAHEAD", "0") == "1"
+    lookahead = bool(lookahead) and X0.is_cuda and fused_count and trace is None
+    if lookahead:
+        cnt2 = [count, torch.zeros(4, dtype=torch.int32, device=dev)]
+        cside, hcnt, ev_done, ev_copy = _count_stream(dev)
+        look = None
+        main_count = count
+        while A > 0:
+            s_ = rounds & 1
+            count = cnt2[s_]                       # the slot this round reports into
+            one_round(A, idx, idx32, first, nrun)
+            main = torch.cuda.current_stream(dev)
+            ev_done[s_].record(main)
+            with torch.cuda.stream(cside):
+                cside.wait_event(ev_done[s_])
+                hcnt[s_:s_ + 1].copy_(count[2:3], non_blocking=True)
+                ev_copy[s_].record(cside)
+            first = 0
+            rounds += 1
+            prev, look = look, s_
+            if prev is None and rounds < max_nfev:
+                continue
+            if prev is None:                       # budget exhausted on the first look
+                prev, look = s_, None
+            ev_copy[prev].synchronize()            # waits for the round BEFORE the one in flight
+            nrun = int(hcnt[prev])
+            if nrun == 0:
+                break
+            if nrun <= compact_below * A:
+                A, idx, idx32 = compact(A, idx32, None)
+                nrun = A
+                look = None                        # counts in flight refer to the old slots
+                if A == 0:
+                    break
+            if use_graph and A <= tail_below:
+                count = main_count
+                r, done = graph_tail(A, idx, idx32, nrun)
+                rounds += r
+                if done:
+                    break
+                use_graph = False                  # not capturable: eager
+                look = None
+            if rounds > max_nfev + 3:              # cannot happen
+                raise RuntimeError("batched driver failed to terminate")
+        count = main_count
+    while not lookahead and A > 0:
         one_round(A, idx, idx32, first, nrun)
         first = 0
         rounds += 1
         if trace is not None:
             trace(rounds, idx, Xnew[:A], state, istate)
         # host look at the status flags: every second round while the rounds
-        # are bandwidth-sized (measured 21.3 -> 20.5 ms per C2 solve against
-        # every round; finished problems are skipped inside the kernels, so a
-        # late look only delays a compaction), every 4th once they are
-        # launch-latency sized
+        # are bandwidth-sized, every 4th once they are launch-latency sized
         every = check_every if A > tail_below else max(check_every, 4)
         if rounds % every == 0 or rounds >= max_nfev:
             if not fused_count:
@@ -431,32 +533,7 @@ def solve_batched(lib, method, fun, jac, X0, lb, ub, ftol, xtol, gtol,
             if nrun == 0:
                 break
             if nrun <= compact_below * A:
-                # ordered compaction on the device (3 small launches, no host
-                # round trip) into the other half of a ping-pong pair
-                if pong is None:
-                    pong = [dict(X=torch.empty_like(Xnew),
-                                 J=None if Xjac is None else torch.empty_like(Xjac),
-                                 i32=torch.empty(A, dtype=torch.int32, device=dev),
-                                 i64=torch.empty(A, dtype=torch.int64, device=dev)),
-                            dict(X=Xnew, J=Xjac,
-                                 i32=torch.empty(A, dtype=torch.int32, device=dev),
-                                 i64=torch.empty(A, dtype=torch.int64, device=dev))]
-                    cwork = torch.empty(int(lib._dll.blsq_compact_work_size(A)),
-                                        dtype=torch.int32, device=dev)
-                o = pong[flip]
-                flip ^= 1
-                lib.call("blsq_compact_batched", A,
-                         None if idx32 is None else idx32.data_ptr(),
-                         istate.data_ptr(), n, Xnew.data_ptr(),
-                         None if Xjac is None else Xjac.data_ptr(),
-                         o["i32"].data_ptr(), o["i64"].data_ptr(),
-                         o["X"].data_ptr(),
-                         None if Xjac is None else o["J"].data_ptr(),
-                         cwork.data_ptr(), lib.stream(X0))
-                launches += 3
-                Xnew, Xjac = o["X"], o["J"]
-                idx, idx32 = o["i64"][:nrun], o["i32"][:nrun]
-                A = nrun
+                A, idx, idx32 = compact(A, idx32, nrun)
             if use_graph and A <= tail_below:
                 r, done = graph_tail(A, idx, idx32, nrun)
                 rounds += r

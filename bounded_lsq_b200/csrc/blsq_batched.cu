@@ -587,6 +587,7 @@ compact_scan_kernel(int nblocks, int32_t* __restrict__ bsum) {
     if (threadIdx.x == 0) {
         int run = 0;
         for (int t = 0; t < 1024; t++) { const int v = part[t]; part[t] = run; run += v; }
+        bsum[nblocks] = run;            // the number of survivors, for the host
     }
     __syncthreads();
     int run = part[threadIdx.x];

@@ -183,7 +183,8 @@ int blsq_count_running(int64_t A, const int32_t* idx, const int32_t* istate,
  * whose problem is still running keep their order: idx_out[k] (int32) and
  * idx64_out[k] (nullable, for torch gathers) = problem id of the k-th
  * survivor, Xnew_out / Xjac_out (k, n) its trial points (Xjac nullable).  The
- * outputs must not alias the inputs.  work: blsq_compact_work_size(A) int32. */
+ * outputs must not alias the inputs.  work: blsq_compact_work_size(A) int32;
+ * its LAST element receives the number of survivors. */
 int64_t blsq_compact_work_size(int64_t A);
 int blsq_compact_batched(int64_t A, const int32_t* idx, const int32_t* istate, int n,
                          const double* Xnew, const double* Xjac, int32_t* idx_out,

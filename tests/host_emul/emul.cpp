@@ -383,7 +383,7 @@ int64_t blsq_compact_work_size(int64_t A) { return A < 0 ? BLSQ_E_BADARG : A / 1
 int blsq_compact_batched(int64_t A, const int32_t* idx, const int32_t* istate, int n,
                          const double* Xnew, const double* Xjac, int32_t* idx_out,
                          int64_t* idx64_out, double* Xnew_out, double* Xjac_out,
-                         int32_t*, void*) {
+                         int32_t* work, void*) {
     int64_t pos = 0;
     for (int64_t s = 0; s < A; s++) {
         const int64_t pid = idx ? idx[s] : s;
@@ -396,6 +396,7 @@ int blsq_compact_batched(int64_t A, const int32_t* idx, const int32_t* istate, i
         }
         pos++;
     }
+    if (work) work[blsq_compact_work_size(A) - 1] = (int32_t)pos;
     return 0;
 }
 
