@@ -208,6 +208,9 @@ def _least_squares_batched(lib, fun, x0, jac, bounds, method, ftol, xtol, gtol,
                         max_nfev, scaling, diff_step=diff_step, **options)
     res = OptimizeResult(out)
     res.fun = cb.f(res.x, None)
+    release = getattr(fun, "blsq_release", None)
+    if callable(release):
+        release()                          # callbacks that cache between fun and jac
     # per-problem texts: res.message[int(res.status[b])]
     res.message = dict(TERMINATION_MESSAGES)
     res.message[L.STATUS_ERR_TR_ZERO] = "ValueError: `s` is zero."

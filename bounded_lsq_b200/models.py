@@ -46,13 +46,18 @@ def callbacks(model_name, jac_kind="exact", lib=None):
             return F, J
 
         def fun(X, idx, y):
+            # F and J come out of one kernel; J is handed to the `jac` call
+            # that follows for the same X and dropped otherwise (the cache
+            # never outlives the next callback: 2 GB at the C2 batch size)
             F, J = run(X, idx, y, jac_kind == "exact")
             last.clear()
-            last[(X.data_ptr(), X.shape[0])] = J
+            if J is not None:
+                last[(X.data_ptr(), X.shape[0])] = J
             return F
 
         def jac(X, idx, y):
             J = last.pop((X.data_ptr(), X.shape[0]), None)
+            last.clear()
             if J is None:
                 _, J = run(X, idx, y, True)
             return J
@@ -72,6 +77,7 @@ def callbacks(model_name, jac_kind="exact", lib=None):
         raise ValueError(model_name)
 
     fun.blsq_indexed = True
+    fun.blsq_release = last.clear          # called by the front end when a solve ends
     if jac is not None:
         jac.blsq_indexed = True
     if jac_kind != "exact":
