@@ -688,10 +688,24 @@ def main():
         c3_line = run_batched(args, WORKLOADS["c3"], "c3", max(2, args.steps // 4),
                               max(1, min(args.warmup, 2)), 1_000_000,
                               cpu_baseline=False)
+        torch.cuda.empty_cache()
+        # NOT the headline: the same C2 solve with the residual model compiled
+        # into the linearisation kernel (J and f never touch HBM) -- what the
+        # solver does when the callback is fusable
+        inl = run_batched(args, w, "c2", max(2, args.steps // 2), 2, w["B"],
+                          cpu_baseline=False, inlined=True)
         if rank == 0:
             line["tall"] = tall_line
             line["tall_asymmetric_start"] = tall_asym
             line["c3"] = c3_line
+            line["c2_inlined_model"] = {
+                "note": "separate record, not the headline: ExpDecay2 compiled into "
+                        "the linearisation kernel (models.callbacks(..., 'inlined')); "
+                        "results bit-identical to the callback path",
+                "value": inl["value"], "unit": inl["unit"],
+                "ms_per_step": inl["ms_per_step"], "e2e": inl["e2e"],
+                "step_frac": inl["roofline"]["step_frac"],
+                "gpu_launches": inl["gpu_launches"], "config": inl["config"]}
             cfg = line["config"]
             cfg["tall_value_it_per_s"] = tall_line["value"]
             cfg["tall_roofline_frac"] = tall_line["roofline"]["frac"]
@@ -706,7 +720,7 @@ def main():
         dist.destroy_process_group()
 
 
-def run_batched(args, w, wname, steps, warmup, B, cpu_baseline=True):
+def run_batched(args, w, wname, steps, warmup, B, cpu_baseline=True, inlined=False):
     """One batched workload on this rank's GPU (problems split by index over
     the ranks, no collective on the data path); returns the JSON record on
     rank 0, None elsewhere."""
@@ -738,10 +752,10 @@ def run_batched(args, w, wname, steps, warmup, B, cpu_baseline=True):
     gen_s = time.perf_counter() - t_gen
 
     fun, jac = model.fun_t, (model.jac_t if w["jac"] == "exact" else "2-point")
-    if args.callbacks == "fused":
+    if args.callbacks == "fused" or inlined:
         try:
             from bounded_lsq_b200 import models as fused
-            fun, jac = fused.callbacks(w["model"], w["jac"])
+            fun, jac = fused.callbacks(w["model"], "inlined" if inlined else w["jac"])
         except Exception as e:          # the fused op is optional sugar
             if rank == 0:
                 print(f"# fused callbacks unavailable ({e!r}); using torch",
@@ -958,7 +972,7 @@ def run_batched(args, w, wname, steps, warmup, B, cpu_baseline=True):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": dict(
-            static_config(w, B, chunk, args.callbacks),
+            static_config(w, B, chunk, "inlined" if inlined else args.callbacks),
             l2="inputs (J+f per round: %.1f GB) exceed the 126 MB L2"
                % (chunk * m * (n + 1) * 8 / 1e9),
             data_pool="%d distinct seeded problems per GPU tiled to %d "

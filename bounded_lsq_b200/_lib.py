@@ -43,6 +43,7 @@ SIGNATURES = {
     "blsq_count_running": [_l, _p, _p, _p, _p],
     "blsq_model_expdecay2": [_l, _p, _i, _p, _p, _p, _p, _p, _p],
     "blsq_model_gausspeak": [_l, _p, _i, _p, _p, _p, _p, _p],
+    "blsq_model_expdecay2_linearise": [_l, _p, _i, _p, _p, _p, _p, _p, _p],
     "blsq_model_linexp_fun": [_l, _i, _p, _p, _p, _p, _p, _p],
     "blsq_model_linexp_jac": [_l, _i, _p, _p, _p, _p],
     "blsq_tall_gram": [_i, _l, _i, _p, _p, _p, _i, _p, _p, _p],

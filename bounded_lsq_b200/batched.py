@@ -80,6 +80,21 @@ class BatchedCallbacks:
         a, k = self._gathered[1]
         return fn(X, *a, **k)
 
+    def lin(self, X, idx32, off, A, p_istate, p_lin, stream):
+        """Models compiled into the linearisation kernel (``fun.blsq_linearise``,
+        bounded_lsq_b200.models): returns m when the callbacks of this round
+        and blsq_linearise_batched were replaced by that one launch, else None."""
+        fn = getattr(self.fun, "blsq_linearise", None)
+        if fn is None:
+            return None
+        sl = slice(off, off + A) if (idx32 is None and (off or A != self.B)) else slice(None)
+
+        def raw(v):
+            return v.tensor[sl] if isinstance(v, PerProblem) else v
+        a = tuple(raw(v) for v in self.args)
+        k = {n: raw(v) for n, v in self.kwargs.items()}
+        return fn(X, idx32, p_istate, p_lin, stream, *a, **k)
+
     def f(self, X, idx):
         return self._call(self.fun, X, idx)
 
@@ -263,51 +278,63 @@ def solve_batched(lib, method, fun, jac, X0, lb, ub, ftol, xtol, gtol,
         p_ub = ub.data_ptr() + off * bstride * 8
         p_xn = Xnew.data_ptr() + off * n * 8
         p_xj = None if Xjac is None else Xjac.data_ptr() + off * n * 8
-        t0 = tick()
-        F = _as_f64(fun(Xa, idx), X0, "fun")
-        if F.dim() != 2 or F.shape[0] != A:
-            raise RuntimeError("batched `fun` must return an (A, m) tensor, "
-                               f"got {tuple(F.shape)} for A={A}")
-        F = F.contiguous()
-        if m is None:
-            m = F.shape[1]
-        elif F.shape[1] != m:
-            raise RuntimeError("`fun` changed its number of residuals")
         ip = None if idx32 is None else idx32.data_ptr()
-        if not fd:
-            J = _as_f64(jac(Xj, idx), X0, "jac")
-            if J.dim() != 3 or J.shape[0] != A or J.shape[2] != n:
-                raise RuntimeError("batched `jac` must return an (A, m, n) "
-                                   f"tensor, got {tuple(J.shape)}")
-            if J.shape[1] != m:
-                raise RuntimeError(
-                    "Inconsistent dimensions between the returns of `fun` "
-                    "and `jac` on the first iteration.")
-            J = J.contiguous()
-            tock("callbacks", t0, nrun)
+        # a model compiled into the linearisation kernel replaces the two
+        # callbacks and blsq_linearise_batched of this round by one launch
+        cbs = getattr(fun, "__self__", None)
+        mm = None
+        if not fd and Xjac is None and hasattr(cbs, "lin"):
             t0 = tick()
-            lib.call("blsq_linearise_batched", A, ip, m, n, F.data_ptr(),
-                     J.data_ptr(), None, None, 0, p_ist, p_lin, stream)
-            tock("linearise", t0, nrun)
-        else:
-            Xpa = Xp.view(-1)[: npts * A * n].view(npts, A, n)
-            lib.call("blsq_fd3_points" if fd3 else "blsq_fd2_points", A, ip, n,
-                     Xj.data_ptr(), p_lb, p_ub, bstride, rel,
-                     Xpa.data_ptr(), dx.data_ptr(), stream)
-            launches += 1
-            Fp = []
-            for i in range(npts):
-                Fi = _as_f64(fun(Xpa[i], idx), X0, "fun").contiguous()
-                if Fi.shape != F.shape:
-                    raise RuntimeError("`fun` changed its output shape")
-                Fp.append(Fi)
-            plist = (C.c_void_p * npts)(*[t.data_ptr() for t in Fp])
-            tock("callbacks", t0, nrun)
+            mm = cbs.lin(Xa, idx32, off, A, p_ist, p_lin, stream)
+            if mm is not None:
+                m = mm
+                launches += 1
+                tock("linearise", t0, nrun)
+        if mm is None:
             t0 = tick()
-            lib.call("blsq_linearise_batched", A, ip, m, n, F.data_ptr(), None,
-                     C.cast(plist, C.c_void_p), dx.data_ptr(), 2 if fd3 else 1,
-                     p_ist, p_lin, stream)
-            tock("linearise", t0, nrun)
+            F = _as_f64(fun(Xa, idx), X0, "fun")
+            if F.dim() != 2 or F.shape[0] != A:
+                raise RuntimeError("batched `fun` must return an (A, m) tensor, "
+                                   f"got {tuple(F.shape)} for A={A}")
+            F = F.contiguous()
+            if m is None:
+                m = F.shape[1]
+            elif F.shape[1] != m:
+                raise RuntimeError("`fun` changed its number of residuals")
+            if not fd:
+                J = _as_f64(jac(Xj, idx), X0, "jac")
+                if J.dim() != 3 or J.shape[0] != A or J.shape[2] != n:
+                    raise RuntimeError("batched `jac` must return an (A, m, n) "
+                                       f"tensor, got {tuple(J.shape)}")
+                if J.shape[1] != m:
+                    raise RuntimeError(
+                        "Inconsistent dimensions between the returns of `fun` "
+                        "and `jac` on the first iteration.")
+                J = J.contiguous()
+                tock("callbacks", t0, nrun)
+                t0 = tick()
+                lib.call("blsq_linearise_batched", A, ip, m, n, F.data_ptr(),
+                         J.data_ptr(), None, None, 0, p_ist, p_lin, stream)
+                tock("linearise", t0, nrun)
+            else:
+                Xpa = Xp.view(-1)[: npts * A * n].view(npts, A, n)
+                lib.call("blsq_fd3_points" if fd3 else "blsq_fd2_points", A, ip, n,
+                         Xj.data_ptr(), p_lb, p_ub, bstride, rel,
+                         Xpa.data_ptr(), dx.data_ptr(), stream)
+                launches += 1
+                Fp = []
+                for i in range(npts):
+                    Fi = _as_f64(fun(Xpa[i], idx), X0, "fun").contiguous()
+                    if Fi.shape != F.shape:
+                        raise RuntimeError("`fun` changed its output shape")
+                    Fp.append(Fi)
+                plist = (C.c_void_p * npts)(*[t.data_ptr() for t in Fp])
+                tock("callbacks", t0, nrun)
+                t0 = tick()
+                lib.call("blsq_linearise_batched", A, ip, m, n, F.data_ptr(), None,
+                         C.cast(plist, C.c_void_p), dx.data_ptr(), 2 if fd3 else 1,
+                         p_ist, p_lin, stream)
+                tock("linearise", t0, nrun)
         t0 = tick()
         lib.call("blsq_round_batched", meth, A, ip, m, n, p_lin,
                  p_x0, p_lb, p_ub, bstride, sc_ptr,
@@ -318,7 +345,8 @@ def solve_batched(lib, method, fun, jac, X0, lb, ub, ftol, xtol, gtol,
         tock("round", t0, nrun)
         if timers is not None:
             timers["shape"] = (n, m, LS, S)
-        launches += 2 if (rwork is None or A < TWO_KERNELS_ABOVE) else 3
+        launches += (2 if (rwork is None or A < TWO_KERNELS_ABOVE) else 3) - \
+            (1 if mm is not None else 0)
 
     def count_separately(A, idx32):
         nonlocal launches

@@ -5,8 +5,33 @@
 
 #include "../../include/blsq.h"
 #include "../../include/blsq_models.h"
+#include "blsq_lin.cuh"
 
 namespace {
+
+// ExpDecay2 compiled INTO the linearisation kernel (lin_kernel MODE 3): the
+// lanes evaluate their rows of f and J in registers -- same operation order
+// as expdecay2_kernel, so the record is bit for bit the one the materialised
+// path produces -- and the 2.5 KB of J and f per problem never touch HBM.
+struct ExpDecay2Rows {
+    const double* t;     // (m)
+    const double* X;     // (A, 4) trial points, by slot
+    const double* y;     // (B, m) data, by problem id
+    int m;
+    template <int N>
+    __device__ __forceinline__ void row(int64_t slot, int64_t pid, int r, double (&a)[N + 1]) const {
+        static_assert(N == 4, "ExpDecay2 has four parameters");
+        const double4 x = *reinterpret_cast<const double4*>(X + slot * 4);
+        const double tr = t[r];
+        const double e1 = exp(-x.y * tr);
+        const double e2 = exp(-x.w * tr);
+        a[0] = e1;
+        a[1] = -x.x * tr * e1;
+        a[2] = e2;
+        a[3] = -x.z * tr * e2;
+        a[4] = x.x * e1 + x.z * e2 - __ldcs(y + pid * m + r);
+    }
+};
 
 __global__ void __launch_bounds__(256)
 expdecay2_kernel(int64_t A, const int64_t* __restrict__ idx, int m,
@@ -193,6 +218,24 @@ bool batched_model_grid(int64_t A, int m, dim3& block, dim3& grid) {
 }  // namespace
 
 extern "C" {
+
+int blsq_model_expdecay2_linearise(int64_t A, const int32_t* idx, int m, const double* t,
+                                   const double* X, const double* y, const int32_t* istate,
+                                   double* lin, void* stream) {
+    using namespace blsq_lin;
+    if (A < 0 || m < 1 || !t || !X || !y || !istate || !lin) return BLSQ_E_BADARG;
+    if (m > 8 * LinCfg<4>::RPL) return BLSQ_E_UNSUPPORTED;      // all rows in one lane group
+    if (A == 0) return 0;
+    ExpDecay2Rows mdl{t, X, y, m};
+    const int64_t blocks = (A * 8 + BLSQ_LIN_THREADS - 1) / BLSQ_LIN_THREADS;
+    if (blocks > 0x7fffffff) return BLSQ_E_UNSUPPORTED;
+    lin_kernel<4, 8, 3, false, ExpDecay2Rows><<<(unsigned)blocks, BLSQ_LIN_THREADS, 0,
+                                                (cudaStream_t)stream>>>(
+        A, idx, m, nullptr, nullptr, PtrList<4>(), nullptr, istate, lin, mdl);
+    cudaError_t e_ = cudaGetLastError();
+    if (e_ != cudaSuccess) return (int)e_;
+    return 0;
+}
 
 int blsq_model_expdecay2(int64_t A, const int64_t* idx, int m, const double* t,
                          const double* X, const double* y, double* F, double* J,

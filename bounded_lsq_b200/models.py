@@ -31,6 +31,7 @@ def callbacks(model_name, jac_kind="exact", lib=None):
     model = getattr(synthetic, model_name)()
     tcache = {}
     last = {}
+    inlined = jac_kind == "inlined"
 
     if model_name == "ExpDecay2":
         def run(X, idx, y, want_j):
@@ -49,7 +50,7 @@ def callbacks(model_name, jac_kind="exact", lib=None):
             # F and J come out of one kernel; J is handed to the `jac` call
             # that follows for the same X and dropped otherwise (the cache
             # never outlives the next callback: 2 GB at the C2 batch size)
-            F, J = run(X, idx, y, jac_kind == "exact")
+            F, J = run(X, idx, y, jac_kind == "exact" and not inlined)
             last.clear()
             if J is not None:
                 last[(X.data_ptr(), X.shape[0])] = J
@@ -76,6 +77,21 @@ def callbacks(model_name, jac_kind="exact", lib=None):
     else:
         raise ValueError(model_name)
 
+    if model_name == "ExpDecay2" and jac_kind == "inlined":
+        if not lib.has("blsq_model_expdecay2_linearise"):
+            raise L.BlsqError("library built without the inlined ExpDecay2 linearisation")
+
+        def linearise(X, idx32, p_istate, p_lin, stream, y):
+            """The lin records of the trial points X straight from (X, t, y): the
+            model is compiled into the linearisation kernel, J and f never
+            touch HBM.  Same bits as fun + jac + blsq_linearise_batched."""
+            t = _t_on(model, X.device, tcache)
+            lib.call("blsq_model_expdecay2_linearise", X.shape[0],
+                     None if idx32 is None else idx32.data_ptr(), model.m,
+                     t.data_ptr(), X.data_ptr(), y.data_ptr(), p_istate, p_lin, stream)
+            return model.m
+        fun.blsq_linearise = linearise
+        jac_kind = "exact"
     fun.blsq_indexed = True
     fun.blsq_release = last.clear          # called by the front end when a solve ends
     if jac is not None:

@@ -22,6 +22,13 @@ extern "C" {
 int blsq_model_expdecay2(int64_t A, const int64_t* idx, int m, const double* t,
                          const double* X, const double* y, double* F, double* J,
                          void* stream);
+/* The same model compiled INTO the linearisation kernel: the lin records of
+ * blsq_linearise_batched (include/blsq.h) for the A trial points X, without
+ * F and J ever being written to memory.  idx: int32 problem ids of the slots
+ * (nullable), as for blsq_linearise_batched.  m <= 64. */
+int blsq_model_expdecay2_linearise(int64_t A, const int32_t* idx, int m, const double* t,
+                                   const double* X, const double* y, const int32_t* istate,
+                                   double* lin, void* stream);
 /* y = A e^{-((t-mu)/sigma)^2/2} + c0 + c1 t + c2 t^2: F (A, m) */
 int blsq_model_gausspeak(int64_t A, const int64_t* idx, int m, const double* t,
                          const double* X, const double* y, double* F,

@@ -175,6 +175,33 @@ def test_fused_model_callbacks_bit_identical(lib, dev):
     assert cases.bits(r1.nfev.cpu().numpy(), r2.nfev.cpu().numpy())
 
 
+def test_inlined_model_bit_identical(lib, dev):
+    """models.callbacks('ExpDecay2', 'inlined'): the model compiled into the
+    linearisation kernel (J and f never in HBM) gives the bits of the callback
+    path, also after compaction, in the graph tail and with staged host inputs."""
+    from bounded_lsq_b200 import models, least_squares_batched, PerProblem
+    from bounded_lsq_b200.synthetic import ExpDecay2
+    model = ExpDecay2()
+    B = 70000
+    _, y = model.make_data(4096, seed=21)
+    yb = cases.T(np.tile(y, (B // 4096 + 1, 1))[:B], dev)
+    X0 = cases.T(np.tile(model.x0, (B, 1)), dev)
+    f0, j0 = models.callbacks("ExpDecay2", "exact")
+    f1, j1 = models.callbacks("ExpDecay2", "inlined")
+    r0 = least_squares_batched(f0, X0, jac=j0, bounds=(model.lb, model.ub), method="trf",
+                               args=(PerProblem(yb),))
+    r1 = least_squares_batched(f1, X0, jac=j1, bounds=(model.lb, model.ub), method="trf",
+                               args=(PerProblem(yb),))
+    r2 = least_squares_batched(f1, X0.cpu().pin_memory(), jac=j1, bounds=(model.lb, model.ub),
+                               method="trf", args=(PerProblem(yb.cpu().pin_memory()),),
+                               options=dict(h2d_chunks=1, prologue_rounds=3))
+    assert r1.kernel_launches < r0.kernel_launches
+    for r in (r1, r2):
+        for fld in ("x", "obj_value", "status", "nfev", "njev", "active_mask"):
+            assert cases.bits(getattr(r, fld).cpu().numpy(), getattr(r0, fld).cpu().numpy()), fld
+    assert int((r0.status > 0).sum()) == B
+
+
 # ------------------------------------------------------------------ tall --
 
 @pytest.mark.parametrize("tag", ["a", "b", "c", "d"])
