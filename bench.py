@@ -955,7 +955,9 @@ def run_batched(args, w, wname, steps, warmup, B, cpu_baseline=True, inlined=Fal
 
     cpu = None
     if cpu_baseline:
-        per_core = 48 if w["jac"] == "exact" else 24
+        # ~10 core-seconds of oracle work (the reference arm's step is 256 / core)
+        per_core = 512 if w["jac"] == "exact" else 128
+        cpu_fits_per_second(w, 16)                 # pool created and warmed untimed
         v, cores, fits, nf = cpu_fits_per_second(w, per_core)
         cpu = {"value": v, "unit": "fits/s", "cores": cores, "kind": "port",
                "sample": f"{fits} fits ({per_core}/core), oracle/blsq_oracle.py"
