@@ -297,8 +297,20 @@ def _stage_host_inputs(x0, args, kwargs, options):
     return stage_host_inputs(x0, args, kwargs, device=dev, h2d_chunks=nch)
 
 
-def _single_callbacks(fun, jac, args, kwargs, dev):
+# A single problem with n <= 8 goes to the batched kernels (B = 1) unless it is
+# tall: from this many rows on, the row-sharded Gram kernels of tall mode
+# (n >= 2) are the faster path -- one warp folding m rows chunk by chunk is not.
+TALL_FROM_ROWS = 32768
+
+
+class _RouteToTall(Exception):
+    """Raised by the first residual evaluation of a B = 1 batched solve when m
+    turns out to be tall (m is only known once `fun` has been called)."""
+
+
+def _single_callbacks(fun, jac, args, kwargs, dev, tall_from=None):
     """least_squares.py:351-371 on top of the (A=1, ...) batched protocol."""
+    seen = [tall_from is None]
 
     def fun_b(X, idx=None):
         f = fun(X[0], *args, **kwargs)
@@ -307,6 +319,10 @@ def _single_callbacks(fun, jac, args, kwargs, dev):
             f = f.reshape(1)
         if f.dim() > 1:
             raise RuntimeError("`fun` must return at most 1-d array_like.")
+        if not seen[0]:
+            seen[0] = True
+            if f.shape[0] >= tall_from:
+                raise _RouteToTall()
         return f.reshape(1, -1)
 
     if not callable(jac):
@@ -339,6 +355,14 @@ def least_squares(fun, x0, jac='2-point', bounds=(-float('inf'), float('inf')),
     unset, trf.py:261,358); ``options={'x_covariance': True}`` fills it with
     the field's documented meaning (least_squares.py:248-252: the inverse of
     J^T J at the solution) from the triangular factor the solve already holds.
+
+    Kernels: n <= 8 runs on the batched kernels (B = 1) and n > 8 on the tall
+    ones; a problem with 2 <= n <= 8 and TALL_FROM_ROWS or more residuals is
+    moved to the tall kernels after its first residual evaluation (that one
+    call is repeated; the solve is then local to this process).
+    ``options={'mode': 'batched' | 'tall'}`` pins the choice; with
+    ``mode='tall'`` and an initialised process group the callbacks return this
+    rank's rows, as for n > 8.
     """
     lib = _lib if _lib is not None else L.get_lib()
     _validate_common(method, bounds, jac)
@@ -372,19 +396,46 @@ def _least_squares(lib, fun, x0, jac, bounds, method, ftol, xtol, gtol, max_nfev
     if not bool(lib.in_bounds(X0, lb, ub).all().item()):
         raise ValueError("`x0` is infeasible.")
 
-    if n > L.MAX_BATCHED_N:
+    # options['mode'] = 'batched' | 'tall' pins the kernels; by default n and
+    # (for 2 <= n <= 8) the number of residuals decide
+    options = dict(options)
+    mode = options.pop("mode", None)
+    if mode not in (None, "batched", "tall"):
+        raise ValueError("`options['mode']` must be 'batched' or 'tall'.")
+    if mode == "batched" and n > L.MAX_BATCHED_N:
+        raise ValueError("batched mode supports n <= %d" % L.MAX_BATCHED_N)
+    if mode == "tall" and n < 2:
+        raise ValueError("tall mode needs n >= 2")
+
+    def tall():
         from .tall import solve_tall
         return solve_tall(lib, method, fun, jac, x0, lb, ub, ftol, xtol, gtol,
                           max_nfev, scaling, diff_step, args, kwargs, options)
 
-    fun_b, jac_b = _single_callbacks(fun, jac, tuple(args), dict(kwargs), dev)
+    if n > L.MAX_BATCHED_N or mode == "tall":
+        return tall()
+
+    probe = TALL_FROM_ROWS if (mode is None and n >= 2 and
+                               not {"trace", "timers"} & set(options)) else None
+    fun_b, jac_b = _single_callbacks(fun, jac, tuple(args), dict(kwargs), dev, probe)
     # single-problem callbacks are arbitrary user Python (often with host
     # round trips): no CUDA-graph capture unless asked for
-    options = dict(options)
     options.setdefault("graph_tail_rounds", 0)
-    out = solve_batched(lib, method, fun_b, jac_b, X0, lb, ub, ftol, xtol,
-                        gtol, max_nfev, scaling, diff_step=diff_step,
-                        **options)
+    try:
+        out = solve_batched(lib, method, fun_b, jac_b, X0, lb, ub, ftol, xtol,
+                            gtol, max_nfev, scaling, diff_step=diff_step,
+                            **options)
+    except _RouteToTall:
+        # m >= TALL_FROM_ROWS: the solve restarts in tall mode (one residual
+        # evaluation at x0 was spent to learn m)
+        options.pop("graph_tail_rounds", None)
+        for k in ("check_every", "compact_below", "tail_below", "prologue",
+                  "prologue_rounds", "lookahead"):
+            options.pop(k, None)
+        # the decision was taken from this process's rows alone, so the solve
+        # is local too; rows sharded over ranks need mode='tall' (or n > 8)
+        options.setdefault("group", False)
+        return tall()
     x = out["x"][0]
     cov = out["x_covariance"]
     if cov is not None:

@@ -30,6 +30,8 @@ from . import _lib as L
 
 def _dist(group):
     import torch.distributed as dist
+    if group is False:                    # this process alone, whatever is initialised
+        return None, 1, 0
     if group is None and not (dist.is_available() and dist.is_initialized()):
         return None, 1, 0
     return dist, dist.get_world_size(group), dist.get_rank(group)

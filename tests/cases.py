@@ -10,6 +10,7 @@ import os
 import warnings
 
 import numpy as np
+import pytest
 import torch
 
 from bounded_lsq_b200 import least_squares, least_squares_batched, PerProblem
@@ -1192,3 +1193,76 @@ def check_x_covariance(lib, dev):
     r2 = least_squares(lambda x: A @ x - 1.0, T([0.0, 0.0], dev), jac=lambda x: A,
                        options=dict(x_covariance=True), _lib=lib)
     assert r2.x_covariance is None
+
+
+def check_mode_routing(lib, dev):
+    """A single problem with n <= 8 runs on the batched kernels unless it is
+    tall: from least_squares.TALL_FROM_ROWS residuals on it goes to the tall
+    kernels (n >= 2), as does options={'mode': 'tall'}; both routes agree with
+    the oracle (status, nfev, active set; x and cost to 1e-8)."""
+    from oracle import blsq_oracle as orc
+    import importlib
+    ls_mod = importlib.import_module("bounded_lsq_b200.least_squares")
+    rng = np.random.default_rng(5)
+    n = 4
+    out = {}
+    for m, jac_kind in ((ls_mod.TALL_FROM_ROWS + 37, "exact"), (600, "exact"),
+                        (ls_mod.TALL_FROM_ROWS, "2-point")):
+        t = np.linspace(0.0, 4.0, m)
+        truth = np.array([2.0, 0.9, 1.2, 3.0])
+        y = truth[0] * np.exp(-truth[1] * t) + truth[2] * np.exp(-truth[3] * t) \
+            + 0.01 * rng.standard_normal(m)
+        lb = np.array([0.0, 0.0, 0.0, 0.0])
+        ub = np.array([10.0, 1.0, 1.1, 10.0])        # the third bound ends up active
+        x0 = np.array([1.0, 0.5, 0.5, 2.0])
+        tt, yt = T(t, dev), T(y, dev)
+        calls = [0]
+
+        def fun_t(x):
+            calls[0] += 1
+            return x[0] * torch.exp(-x[1] * tt) + x[2] * torch.exp(-x[3] * tt) - yt
+
+        def jac_t(x):
+            e1, e2 = torch.exp(-x[1] * tt), torch.exp(-x[3] * tt)
+            return torch.stack([e1, -x[0] * tt * e1, e2, -x[2] * tt * e2], dim=1)
+
+        def fun_n(x):
+            return x[0] * np.exp(-x[1] * t) + x[2] * np.exp(-x[3] * t) - y
+
+        def jac_n(x):
+            e1, e2 = np.exp(-x[1] * t), np.exp(-x[3] * t)
+            return np.stack([e1, -x[0] * t * e1, e2, -x[2] * t * e2], axis=1)
+        for method in ("trf", "dogbox"):
+            ref = orc.least_squares(fun_n, x0, jac=jac_n if jac_kind == "exact" else "2-point",
+                                    bounds=(lb, ub), method=method)
+            kw = dict(jac=jac_t if jac_kind == "exact" else "2-point",
+                      bounds=(T(lb, dev), T(ub, dev)), method=method, _lib=lib)
+            routes = {}
+            for mode in (None, "batched", "tall"):
+                if mode == "batched" and m > 4096:
+                    continue                           # the slow route this replaces
+                calls[0] = 0
+                res = least_squares(fun_t, T(x0, dev), options=dict(mode=mode) if mode else {},
+                                    **kw)
+                routes[mode] = (res, calls[0])
+                x = res.x.cpu().numpy()
+                tol = 1e-8 if jac_kind == "exact" else 1e-6
+                assert res.status == ref.status, (m, method, mode, res.status, ref.status)
+                if jac_kind == "exact":
+                    assert res.nfev == ref.nfev and res.njev == ref.njev, (m, method, mode)
+                assert np.array_equal(res.active_mask.cpu().numpy(), ref.active_mask)
+                assert np.abs(x - ref.x).max() <= tol * np.abs(ref.x).max(), (m, method, mode)
+                assert abs(res.obj_value - ref.obj_value) <= tol * ref.obj_value
+            # the automatic route is the tall one exactly when m is tall, and
+            # costs one residual evaluation more than asking for it
+            auto, tall = routes[None], routes["tall"]
+            if m >= ls_mod.TALL_FROM_ROWS:
+                assert bits(auto[0].x.cpu().numpy(), tall[0].x.cpu().numpy())
+                assert auto[1] == tall[1] + 1, (auto[1], tall[1])
+            else:
+                assert bits(auto[0].x.cpu().numpy(), routes["batched"][0].x.cpu().numpy())
+                assert auto[1] == routes["batched"][1]
+            out[(m, jac_kind, method)] = (auto[0].status, auto[0].nfev)
+    with pytest.raises(ValueError):
+        least_squares(fun_t, T(x0, dev), options=dict(mode="wide"), _lib=lib)
+    return out

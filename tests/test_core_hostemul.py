@@ -104,6 +104,10 @@ def test_x_covariance(lib):
     cases.check_x_covariance(lib, DEV)
 
 
+def test_mode_routing(lib):
+    cases.check_mode_routing(lib, DEV)
+
+
 def test_compact_batched(lib):
     cases.check_compact_batched(lib, DEV)
 

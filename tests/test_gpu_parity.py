@@ -279,6 +279,10 @@ def test_x_covariance(lib, dev):
     cases.check_x_covariance(lib, dev)
 
 
+def test_mode_routing(lib, dev):
+    cases.check_mode_routing(lib, dev)
+
+
 def test_compact_batched(lib, dev):
     cases.check_compact_batched(lib, dev)
 
