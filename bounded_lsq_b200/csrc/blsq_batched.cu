@@ -585,3 +585,15 @@ int blsq_compact_batched(int64_t A, const int32_t* idx, const int32_t* istate, i
 
 }  // extern "C"
 
+#ifdef BLSQ_PHASE_CLOCKS
+// tools/phase_probe.py only: cycles [0..15] and visits [16..31] per phase of
+// trf_round_impl since the last reset
+extern "C" int blsq_debug_phase_read(unsigned long long* out, int reset) {
+    cudaError_t e = cudaMemcpyFromSymbol(out, blsq_phase_acc, sizeof(blsq_phase_acc));
+    if (e == cudaSuccess && reset) {
+        unsigned long long z[32] = {0};
+        e = cudaMemcpyToSymbol(blsq_phase_acc, z, sizeof(z));
+    }
+    return (int)e;
+}
+#endif

@@ -26,6 +26,25 @@
 
 #if defined(__CUDACC__)
 #define BLSQ_HD __host__ __device__ __forceinline__
+
+// tools/phase_probe.py builds a variant with -DBLSQ_PHASE_CLOCKS: cycles per
+// phase of trf_round_impl, summed over all threads (never in the shipped .so)
+#if defined(BLSQ_PHASE_CLOCKS) && defined(__CUDACC__)
+static __device__ unsigned long long blsq_phase_acc[32];
+#endif
+#if defined(BLSQ_PHASE_CLOCKS) && defined(__CUDA_ARCH__)
+#define BLSQ_PHASE_BEGIN long long ph_ = clock64()
+#define BLSQ_PHASE(k)                                                          \
+    do {                                                                       \
+        long long c_ = clock64();                                              \
+        atomicAdd(&blsq_phase_acc[k], (unsigned long long)(c_ - ph_));         \
+        atomicAdd(&blsq_phase_acc[16 + k], 1ull);                              \
+        ph_ = clock64();                                                       \
+    } while (0)
+#else
+#define BLSQ_PHASE_BEGIN
+#define BLSQ_PHASE(k)
+#endif
 #define BLSQ_UNROLL _Pragma("unroll")
 #else
 #define BLSQ_HD inline
@@ -788,6 +807,7 @@ BLSQ_HD int trf_round_impl(double* sp, int* ist, const double* lp,
     constexpr int NP = S::NP;
     int status = ST_RUNNING;     // pending status set by the inner loop
     bool adopt = false;
+    BLSQ_PHASE_BEGIN;
     double sc[8];                // DELTA ALPHA PRED CORR NSTEPH NSTEP GNORM -
     ld_block<8>(sp + S::SCAL, sc);
     double blk[L::SIZE];         // R, QTF, G, OBJ of the point the round works at
@@ -862,6 +882,7 @@ BLSQ_HD int trf_round_impl(double* sp, int* ist, const double* lp,
         return 0;
     }
 
+    BLSQ_PHASE(0);
     // ---- linearise (trf.py:239-277) at x ----
     const double* Rm = blk + L::R;
     double scale[NP], d[N], g_h[N], diag_h[N], v[N];
@@ -929,6 +950,7 @@ BLSQ_HD int trf_round_impl(double* sp, int* ist, const double* lp,
     double theta = 1.0 - g_norm;
     if (theta < 0.995) theta = 0.995;
 
+    BLSQ_PHASE(1);
     // ---- propose (trf.py:284-308) ----
     const double Delta = sc[0];
     double alpha = sc[1];
@@ -943,10 +965,12 @@ BLSQ_HD int trf_round_impl(double* sp, int* ist, const double* lp,
                 A[tri_index<N>(i, j)] = Rm[tri_index<N>(i, j)] * d[j];
         }
         hat_fold_packed<N>(A, b, diag_h);
+        BLSQ_PHASE(2);
         // every mode takes the same decision with the same arithmetic, so the
         // result does not depend on how the driver splits the work
         if (MODE != 2 && gn_shortcut_packed<N>(A, b, P.m, Delta, p_h)) {
             alpha = 0.0;                           // trust_region.py:117
+            BLSQ_PHASE(3);
         } else if (MODE == 1) {
             st_block<8>(sp + S::SCAL, sc);         // Delta / alpha of the judge, g_norm
             return TRF_DEFER;
@@ -965,8 +989,11 @@ BLSQ_HD int trf_round_impl(double* sp, int* ist, const double* lp,
                 zero_col = zero_col || z;
             }
             double sv[N], Vt[N * N], suf[N];
+            BLSQ_PHASE(4);
             hat_finish<N>(Af, b, sv, Vt, suf);
+            BLSQ_PHASE(5);
             solve_lsq_trust_region<N>(P.m, suf, sv, Vt, Delta, alpha, p_h, zero_col);
+            BLSQ_PHASE(6);
         }
     }
     sc[1] = alpha;
@@ -1047,6 +1074,7 @@ BLSQ_HD int trf_round_impl(double* sp, int* ist, const double* lp,
         for (int i = 0; i < N; i++)
             step_h[i] = (k == 0) ? p_h[i] : (k == 1 ? refl[i] : c_h[i]);
     }
+    BLSQ_PHASE(7);
     double xn[NP];
     double corr = 0.0, nsh2 = 0.0, ns2 = 0.0;
     BLSQ_UNROLL
@@ -1066,6 +1094,7 @@ BLSQ_HD int trf_round_impl(double* sp, int* ist, const double* lp,
     sc[4] = sqrt(nsh2);
     sc[5] = sqrt(ns2);
     st_block<8>(sp + S::SCAL, sc);
+    BLSQ_PHASE(8);
     return 1;
 }
 

@@ -37,6 +37,20 @@ def run(label, env=None, **opts):
                           launches=r.kernel_launches)), flush=True)
 
 
+if os.environ.get("SWEEP"):
+    # driver thresholds: where the CUDA-graph tail starts, rounds per replay,
+    # compaction threshold
+    run("default")
+    for tb in (16384, 32768, 65536, 131072):
+        run("tail_below=%d" % tb, tail_below=tb)
+    for gr in (4, 16, 32):
+        run("graph_tail_rounds=%d" % gr, graph_tail_rounds=gr)
+    for tb, gr in ((32768, 16), (65536, 16)):
+        run("tail_below=%d graph_tail_rounds=%d" % (tb, gr), tail_below=tb, graph_tail_rounds=gr)
+    for cb in (0.5, 0.65, 0.85, 0.92):
+        run("compact_below=%.2f" % cb, compact_below=cb)
+    sys.exit(0)
+
 run("default")
 run("separate count kernel", env={"BLSQ_ROUND_COUNT": "0"})
 run("no graph tail", graph_tail_rounds=0)
