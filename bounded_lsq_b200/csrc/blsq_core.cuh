@@ -27,6 +27,12 @@
 #if defined(__CUDACC__)
 #define BLSQ_HD __host__ __device__ __forceinline__
 
+#define BLSQ_UNROLL _Pragma("unroll")
+#else
+#define BLSQ_HD inline
+#define BLSQ_UNROLL
+#endif
+
 // tools/phase_probe.py builds a variant with -DBLSQ_PHASE_CLOCKS: cycles per
 // phase of trf_round_impl, summed over all threads (never in the shipped .so)
 #if defined(BLSQ_PHASE_CLOCKS) && defined(__CUDACC__)
@@ -44,11 +50,6 @@ static __device__ unsigned long long blsq_phase_acc[32];
 #else
 #define BLSQ_PHASE_BEGIN
 #define BLSQ_PHASE(k)
-#endif
-#define BLSQ_UNROLL _Pragma("unroll")
-#else
-#define BLSQ_HD inline
-#define BLSQ_UNROLL
 #endif
 
 namespace blsq {
