@@ -885,21 +885,44 @@ def run_batched(args, w, wname, steps, warmup, B, cpu_baseline=True, inlined=Fal
                                               method=method, args=aa, options=opts))
         return outs
 
-    solve_staged(stage(0))                 # untimed: copy stream, first capture
+    # results go back on their own stream into one of two pinned sets: the
+    # device-to-host copies of step k run under the solve of step k + 1, the
+    # host has step k's results before step k + 1 ends
+    back = torch.cuda.Stream(dev)
+    outsets = [(x_out, st_out, obj_out),
+               (torch.empty_like(x_out).pin_memory(), torch.empty_like(st_out).pin_memory(),
+                torch.empty_like(obj_out).pin_memory())]
+
+    def results_to_host(outs, k):
+        xo, so, oo = outsets[k % 2]
+        ev = torch.cuda.Event()
+        back.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(back):
+            for c, o in enumerate(outs):
+                sl = slice(c * chunk, c * chunk + o.x.shape[0])
+                xo[sl].copy_(o.x, non_blocking=True)
+                so[sl].copy_(o.status, non_blocking=True)
+                oo[sl].copy_(o.obj_value, non_blocking=True)
+            ev.record(back)
+        return ev, outs                    # `outs` stays referenced until the copies are done
+
+    results_to_host(solve_staged(stage(0)), 0)[0].synchronize()   # untimed: streams, first capture
     barrier()
     e2 = torch.cuda.Event(enable_timing=True)
     e3 = torch.cuda.Event(enable_timing=True)
     e2.record()
     st = stage(0)
+    pending = None
     for k in range(steps):
         nxt = stage(k + 1) if k + 1 < steps else None
         outs = solve_staged(st)
-        x_out.copy_(torch.cat([o.x for o in outs]), non_blocking=True)
-        st_out.copy_(torch.cat([o.status for o in outs]), non_blocking=True)
-        obj_out.copy_(torch.cat([o.obj_value for o in outs]), non_blocking=True)
-        torch.cuda.current_stream(dev).synchronize()      # results are on the host
+        if pending is not None:
+            pending[0].synchronize()       # step k - 1 is on the host
+        pending = results_to_host(outs, k)
         st = nxt
+    pending[0].synchronize()               # the last step's results are on the host
     e3.record()
+    torch.cuda.current_stream(dev).synchronize()
     barrier()
     e2e_ms = reduce_max(e2.elapsed_time(e3))
     e2e_value = world * B * steps / (e2e_ms * 1e-3)
@@ -987,7 +1010,10 @@ def run_batched(args, w, wname, steps, warmup, B, cpu_baseline=True, inlined=Fal
                 "ms_per_step": e2e_ms / steps,
                 "pipeline": "stage_host_inputs: pinned x0 / y -> device in %d chunks on a "
                             "copy stream, each chunk starts its rounds when it lands; the "
-                            "copies of step k+1 are started before step k is solved" % nch},
+                            "copies of step k+1 are started before step k is solved and the "
+                            "results of step k return to pinned memory under step k+1 (own "
+                            "stream, two buffer sets); the region ends when the last "
+                            "results are on the host" % nch},
         "gpu_launches": launches,
         "roofline": roofline,
         "cpu_baseline": cpu,

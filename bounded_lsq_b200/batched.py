@@ -447,6 +447,11 @@ def solve_batched(lib, method, fun, jac, X0, lb, ub, ftol, xtol, gtol,
         # chunks; each chunk runs its first rounds alone while the next one is
         # still on the wire, then the whole batch carries on in lock step
         K = max(1, min(int(prologue_rounds), max_nfev))
+        if all(ev is None or ev.query() for _, _, ev in prologue):
+            # everything has landed already (a pipelined caller staged this
+            # batch under the previous solve): one lock-step start, full-size
+            # launches
+            prologue = [(0, B, None)]
         for c0, c1, ev in prologue:
             if ev is not None:
                 torch.cuda.current_stream(dev).wait_event(ev)
