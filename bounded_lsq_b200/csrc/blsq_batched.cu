@@ -43,6 +43,21 @@ namespace {
 // MODE 1 runs the round with the Gauss-Newton shortcut and appends the slots
 // that need the SVD route to work[1..] (work[0] = their number); MODE 2 then
 // finishes exactly those slots with dense warps (blsq_core.cuh trf_round_impl).
+// 1: L2 prefetch of the TRF records at the top of the round (C2 full-batch
+// round 0.248 -> 0.215 ms per 1e6 problems, profiles/r2_kbench_prefetch.jsonl).
+// Measured against it and dropped: the same prefetch into L1 (no different), a
+// one-wave grid striding over the slots and prefetching one slot ahead
+// (0.313 ms), and staging both records through shared memory with 16-byte
+// cp.async copies (0.266 ms).
+#ifndef BLSQ_ROUND_PREFETCH
+#define BLSQ_ROUND_PREFETCH 1
+#endif
+#if BLSQ_ROUND_PREFETCH == 2
+#define BLSQ_PREFETCH(p) asm volatile("prefetch.global.L1 [%0];" ::"l"(p))
+#else
+#define BLSQ_PREFETCH(p) asm volatile("prefetch.global.L2 [%0];" ::"l"(p))
+#endif
+
 template <int N, int METHOD, int MODE>
 __device__ __forceinline__ bool
 round_slot(int64_t slot, int64_t A, const int32_t* __restrict__ idx,
@@ -62,6 +77,23 @@ round_slot(int64_t slot, int64_t A, const int32_t* __restrict__ idx,
 #pragma unroll
     for (int i = 0; i < N; i++) sc[i] = scaling ? scaling[i] : 1.0;
     if (METHOD == BLSQ_METHOD_TRF) {
+#if BLSQ_ROUND_PREFETCH
+        // every line of the two records is requested NOW: the round reads them
+        // block by block behind data-dependent branches, and at 16 warps per
+        // SM one DRAM round trip per block is what the kernel waits for
+        {
+            const char* s0 = reinterpret_cast<const char*>(state + pid * (int64_t)SS);
+            const char* l0 = reinterpret_cast<const char*>(lin + slot * (int64_t)L::SIZE);
+#pragma unroll
+            for (int o = 0; o < SS * 8; o += 128) BLSQ_PREFETCH(s0 + o);
+#pragma unroll
+            for (int o = 0; o < L::SIZE * 8; o += 128) BLSQ_PREFETCH(l0 + o);
+            if (bstride) {
+                BLSQ_PREFETCH(lb + pid * bstride);
+                BLSQ_PREFETCH(ub + pid * bstride);
+            }
+        }
+#endif
         // the records stay in memory: trf_round_impl fetches the blocks it
         // needs when it needs them (256-bit loads) and stores what changed
         int ist[4];
