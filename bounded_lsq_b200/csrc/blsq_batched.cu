@@ -175,10 +175,11 @@ round_slot(int64_t slot, int64_t A, const int32_t* __restrict__ idx,
 
 // CTAs per SM of the round kernel: TRF N <= 4 runs best at 4 x 128 threads
 // (128 registers; 3 x 164 without spills measured 5 % slower), dogbox and the
-// larger N at 3 (C3, N = 6 dogbox: 0.60 -> 0.50 ms per 10^6 problems).
+// larger N at 2 (255 registers: C3, N = 6 dogbox, 0.60 ms per 10^6 problems at
+// 4 CTAs, 0.50 at 3, 0.44 at 2 where it no longer spills).
 template <int N, int METHOD> struct RoundCfg {
     static constexpr int MINB =
-        (METHOD == BLSQ_METHOD_DOGBOX || N > 4) ? (BLSQ_ROUND_MINB > 3 ? 3 : BLSQ_ROUND_MINB)
+        (METHOD == BLSQ_METHOD_DOGBOX || N > 4) ? (BLSQ_ROUND_MINB > 2 ? 2 : BLSQ_ROUND_MINB)
                                                 : BLSQ_ROUND_MINB;
 };
 
