@@ -33,6 +33,10 @@ struct ExpDecay2Rows {
     }
 };
 
+#ifndef BLSQ_EXPDECAY2_QUADS
+#define BLSQ_EXPDECAY2_QUADS 1
+#endif
+
 __global__ void __launch_bounds__(256)
 expdecay2_kernel(int64_t A, const int64_t* __restrict__ idx, int m,
                  const double* __restrict__ t, const double* __restrict__ X,
@@ -59,6 +63,44 @@ expdecay2_kernel(int64_t A, const int64_t* __restrict__ idx, int m,
                      "d"(j1), "d"(e2), "d"(j3)
                      : "memory");
     }
+}
+
+// m % 4 == 0: one thread per (problem, four consecutive rows): 256-bit loads of
+// t and y, one 256-bit store of F and four of J (128 contiguous bytes)
+__global__ void __launch_bounds__(256)
+expdecay2x4_kernel(int64_t A, const int64_t* __restrict__ idx, int m,
+                   const double* __restrict__ t, const double* __restrict__ X,
+                   const double* __restrict__ y, double* __restrict__ F,
+                   double* __restrict__ J) {
+    const int64_t s = (int64_t)blockIdx.x * blockDim.y + threadIdx.y;
+    const int r = 4 * (blockIdx.y * blockDim.x + threadIdx.x);
+    if (s >= A || r >= m) return;
+    const int64_t g = s * m + r;
+    const int64_t pid = idx ? idx[s] : s;
+    const double4 x = *reinterpret_cast<const double4*>(X + s * 4);
+    double tr[4], yv[4], f[4];
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
+                 : "=d"(tr[0]), "=d"(tr[1]), "=d"(tr[2]), "=d"(tr[3])
+                 : "l"(t + r));
+    asm volatile("ld.global.cs.v4.f64 {%0,%1,%2,%3}, [%4];"
+                 : "=d"(yv[0]), "=d"(yv[1]), "=d"(yv[2]), "=d"(yv[3])
+                 : "l"(y + pid * m + r));
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        // same operation order as synthetic.ExpDecay2.fun_t / jac_t
+        const double e1 = exp(-x.y * tr[k]);
+        const double e2 = exp(-x.w * tr[k]);
+        f[k] = x.x * e1 + x.z * e2 - yv[k];
+        if (J) {
+            const double j1 = -x.x * tr[k] * e1, j3 = -x.z * tr[k] * e2;
+            asm volatile("st.global.cs.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(J + (g + k) * 4),
+                         "d"(e1), "d"(j1), "d"(e2), "d"(j3)
+                         : "memory");
+        }
+    }
+    asm volatile("st.global.cs.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(F + g), "d"(f[0]), "d"(f[1]),
+                 "d"(f[2]), "d"(f[3])
+                 : "memory");
 }
 
 __global__ void __launch_bounds__(256)
@@ -240,6 +282,7 @@ linexp_jac_kernel(int64_t m, int n, double* __restrict__ J, const double* __rest
 // rounded up to a warp, y the problems that fit beside it
 bool batched_model_grid(int64_t A, int m, dim3& block, dim3& grid) {
     int bx = m < 256 ? ((m + 31) / 32) * 32 : 256;
+    if (m < 32 && 32 % m == 0) bx = m;          // several problems per warp
     int by = 256 / bx;
     if (by < 1) by = 1;
     const int64_t gx = (A + by - 1) / by;
@@ -278,8 +321,13 @@ int blsq_model_expdecay2(int64_t A, const int64_t* idx, int m, const double* t,
     if (A < 0 || m < 1 || !t || !X || !y || !F) return BLSQ_E_BADARG;
     if (A == 0) return 0;
     dim3 block, grid;
-    if (!batched_model_grid(A, m, block, grid)) return BLSQ_E_UNSUPPORTED;
-    expdecay2_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(A, idx, m, t, X, y, F, J);
+    const bool quads = BLSQ_EXPDECAY2_QUADS && m % 4 == 0 && ((uintptr_t)t % 32 == 0) &&
+                       ((uintptr_t)y % 32 == 0) && ((uintptr_t)F % 32 == 0);
+    if (!batched_model_grid(A, quads ? m / 4 : m, block, grid)) return BLSQ_E_UNSUPPORTED;
+    if (quads)
+        expdecay2x4_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(A, idx, m, t, X, y, F, J);
+    else
+        expdecay2_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(A, idx, m, t, X, y, F, J);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : (int)e;
 }
