@@ -913,6 +913,7 @@ def run_batched(args, w, wname, steps, warmup, B, cpu_baseline=True, inlined=Fal
     e2.record()
     st = stage(0)
     pending = None
+    marks = [e2]
     for k in range(steps):
         nxt = stage(k + 1) if k + 1 < steps else None
         outs = solve_staged(st)
@@ -920,11 +921,14 @@ def run_batched(args, w, wname, steps, warmup, B, cpu_baseline=True, inlined=Fal
             pending[0].synchronize()       # step k - 1 is on the host
         pending = results_to_host(outs, k)
         st = nxt
+        marks.append(torch.cuda.Event(enable_timing=True))
+        marks[-1].record()
     pending[0].synchronize()               # the last step's results are on the host
     e3.record()
     torch.cuda.current_stream(dev).synchronize()
     barrier()
     e2e_ms = reduce_max(e2.elapsed_time(e3))
+    e2e_steps = [round(a.elapsed_time(b), 3) for a, b in zip(marks, marks[1:])]
     e2e_value = world * B * steps / (e2e_ms * 1e-3)
     h2d = y_host.numel() * 8 + x0_host.numel() * 8
     d2h = x_out.numel() * 8 + st_out.numel() * 8 + obj_out.numel() * 8
@@ -1007,7 +1011,7 @@ def run_batched(args, w, wname, steps, warmup, B, cpu_baseline=True, inlined=Fal
             per_step_ms=[round(v, 3) for v in per_step_ms]),
         "e2e": {"value": e2e_value, "unit": "fits/s",
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": e2e_ms / steps,
+                "ms_per_step": e2e_ms / steps, "per_step_ms": e2e_steps,
                 "pipeline": "stage_host_inputs: pinned x0 / y -> device in %d chunks on a "
                             "copy stream, each chunk starts its rounds when it lands; the "
                             "copies of step k+1 are started before step k is solved and the "
