@@ -37,46 +37,80 @@ namespace {
 constexpr int FAC_THREADS = 1024;
 constexpr int FAC_SMEM_MAX_N = 128;      // n x n doubles in shared memory up to here
 
+// sqrt(d) and 1/sqrt(d) from one reciprocal square root and a Newton step each
+// (within ~1 ulp; d > 0)
+__device__ __forceinline__ void sqrt_terms(double d, double& r, double& inv_r) {
+    double y = rsqrt(d);
+    double rr = d * y;
+    rr = fma(fma(-rr, rr, d), 0.5 * y, rr);
+    y = fma(fma(-rr, y, 1.0), y, y);
+    r = rr;
+    inv_r = y;
+}
+
 // in-place upper Cholesky of the upper triangle of M (n x n, row-major):
 // M = R^T R.  diag0[k] = the diagonal of the matrix before any shift.  A pivot
 // that has collapsed to rounding level (<= 8 n eps diag0[k]) stops the sweep:
 // returns k + 1 (0 = success) and the caller retries with a diagonal shift.
-__device__ int chol_upper(double* M, const double* diag0, int n) {
+// 32 x 32 threads over the trailing block (no index division), two barriers
+// per column: the pivot itself stays in place until the sweep is over (dg
+// collects the diagonal of R), so nobody has to wait for the others to have
+// read it.
+__device__ int chol_upper(double* M, const double* diag0, double* dg, int n) {
     const int tid = threadIdx.x, nt = blockDim.x;
+    const int tx = tid & 31, ty = tid >> 5, ny = nt >> 5;
     const double tol = 8.0 * n * 2.220446049250313e-16;
     for (int k = 0; k < n; k++) {
         const double piv = M[k * n + k];
         if (!(piv > tol * diag0[k])) return k + 1;   // uniform: everyone reads the same value
-        const double r = sqrt(piv);
-        __syncthreads();                            // all have read the pivot
-        for (int j = k + tid; j < n; j += nt) M[k * n + j] = (j == k) ? r : M[k * n + j] / r;
+        double r, inv_r;
+        sqrt_terms(piv, r, inv_r);
+        if (tid == 0) dg[k] = r;
+        for (int j = k + 1 + tid; j < n; j += nt) M[k * n + j] *= inv_r;
         __syncthreads();
-        const int w = n - k - 1;
-        for (int e = tid; e < w * w; e += nt) {
-            const int i = k + 1 + e / w, j = k + 1 + e % w;
-            if (j >= i) M[i * n + j] = fma(-M[k * n + i], M[k * n + j], M[i * n + j]);
+        for (int i = k + 1 + ty; i < n; i += ny) {
+            const double ri = M[k * n + i];
+            for (int j = k + 1 + tx; j < n; j += 32)
+                if (j >= i) M[i * n + j] = fma(-ri, M[k * n + j], M[i * n + j]);
         }
         __syncthreads();
     }
+    for (int k = tid; k < n; k += nt) M[k * n + k] = dg[k];
+    __syncthreads();
     return 0;
 }
 
-// X = R^-1 for upper triangular R; one warp per column (back substitution,
-// lanes over the inner product).  Entries below the diagonal are zeroed.
-__device__ void inv_upper(const double* R, double* X, int n) {
+// X = R^-1 for upper triangular R; one warp per column (back substitution).
+// The column being built stays in registers -- lane l owns its entries
+// k = l, l + 32, ... (n <= 256: 8 per lane) -- so that a step never waits for
+// a value the previous step has just written to memory; invd[i] = 1 / R_ii.
+// Entries below the diagonal are zeroed.
+__device__ void inv_upper(const double* R, double* X, double* invd, int n) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) invd[i] = 1.0 / R[i * n + i];
+    __syncthreads();
     for (int j = warp; j < n; j += nw) {
-        for (int i = n - 1; i > j; i--)
-            if (lane == 0) X[i * n + j] = 0.0;
-        if (lane == 0) X[j * n + j] = 1.0 / R[j * n + j];
-        __syncwarp();
+        double xc[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) xc[q] = (lane + 32 * q == j) ? invd[j] : 0.0;
         for (int i = j - 1; i >= 0; i--) {
             double s = 0.0;
-            for (int k = i + 1 + lane; k <= j; k += 32) s = fma(R[i * n + k], X[k * n + j], s);
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                const int k = lane + 32 * q;
+                if (k > i && k <= j) s = fma(R[i * n + k], xc[q], s);
+            }
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-            if (lane == 0) X[i * n + j] = -s / R[i * n + i];
-            __syncwarp();
+            const double xi = -s * invd[i];
+#pragma unroll
+            for (int q = 0; q < 8; q++)
+                if (lane + 32 * q == i) xc[q] = xi;
+        }
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            const int k = lane + 32 * q;
+            if (k < n) X[k * n + j] = xc[q];          // zero below the diagonal
         }
     }
 }
@@ -112,13 +146,16 @@ tall_factor_kernel(int pass, int n, int nranks, int64_t gstride, const double* _
     double* shifts = fac + FL.SHIFT;
     double* refine = fac + FL.REFINE;
     double* M = use_smem ? fsm : scratch;
+    __shared__ double diag0[256];
+    __shared__ double wrk[256];              // diag(R) / reciprocals / 1/sqrt(diag G)
+    __shared__ double dmax_s;
 
     if (pass == 3) {
         // the factor found so far becomes the preconditioner of another pass
         for (int e = tid; e < n2; e += nt) { R1[e] = R[e]; M[e] = R[e]; }
         __syncthreads();
         double* X = use_smem ? scratch : R;
-        inv_upper(M, X, n);
+        inv_upper(M, X, wrk, n);
         __syncthreads();
         pack_rinv(X, rinvp, n, FL.nb);
         if (tid == 0) { refine[0] = 0.0; info[0] = 0.0; }
@@ -131,8 +168,6 @@ tall_factor_kernel(int pass, int n, int nranks, int64_t gstride, const double* _
     // O(shift1 shift2) I, i.e. the null directions of J come out with a
     // singular value of ~1e-13 |J| instead of 0 and everything else is
     // unchanged to ~1e-14 (shifted CholeskyQR, Fukaya et al. 2020).
-    __shared__ double diag0[256];
-    __shared__ double dmax_s;
     double shift = 0.0;
     int bad = 0;
     for (int attempt = 0; attempt < 12; attempt++) {
@@ -165,16 +200,20 @@ tall_factor_kernel(int pass, int n, int nranks, int64_t gstride, const double* _
             // deficient J (their Y column is noise): no pass can fix those,
             // they are left out of the test.
             const double tiny = 1e-8 * dmax_s;
+            for (int i = tid; i < n; i += nt) wrk[i] = (diag0[i] > tiny) ? rsqrt(diag0[i]) : 0.0;
+            __syncthreads();
             int far = 0;
-            for (int i = tid; i < n; i += nt) {
-                if (!(diag0[i] > tiny)) continue;
+            const int lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+            for (int i = warp; i < n; i += nw) {       // one warp per row
                 double rs = 0.0;
-                for (int j = 0; j < n; j++) {
-                    if (j == i || !(diag0[j] > tiny)) continue;
+                for (int j = lane; j < n; j += 32) {
+                    if (j == i) continue;
                     const double gij = (j > i) ? M[i * n + j] : M[j * n + i];
-                    rs += fabs(gij) / sqrt(diag0[i] * diag0[j]);
+                    rs += fabs(gij) * wrk[j];
                 }
-                if (!(rs <= 0.5)) far = 1;
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) rs += __shfl_xor_sync(0xffffffffu, rs, off);
+                if (wrk[i] > 0.0 && !(rs * wrk[i] <= 0.5)) far = 1;
             }
             // (the spread of the diagonal itself does not matter: Gram and
             // Cholesky errors scale with sqrt(G_ii G_jj) componentwise)
@@ -182,7 +221,7 @@ tall_factor_kernel(int pass, int n, int nranks, int64_t gstride, const double* _
             if (tid == 0) refine[0] = far ? 1.0 : 0.0;
         }
         __syncthreads();
-        bad = chol_upper(M, diag0, n);
+        bad = chol_upper(M, diag0, wrk, n);
         if (!bad) break;
         if (!(dmax_s > 0.0) || dmax_s != dmax_s) break;      // zero or NaN Jacobian
         shift = (shift == 0.0) ? 16.0 * n * 2.220446049250313e-16 * dmax_s : shift * 10.0;
@@ -206,30 +245,49 @@ tall_factor_kernel(int pass, int n, int nranks, int64_t gstride, const double* _
         __syncthreads();
         // dense inverse into a free n x n region, then the fragment order
         double* X = use_smem ? scratch : R;
-        inv_upper(M, X, n);
+        inv_upper(M, X, wrk, n);
         __syncthreads();
         pack_rinv(X, rinvp, n, FL.nb);
         if (tid == 0) info[0] = 0.0;
         return;
     }
-    // pass 2: R = R2 R1 (upper x upper), Q^T f = R2^-T z
-    for (int e = tid; e < n2; e += nt) {
-        const int i = e / n, j = e % n;
-        double s = 0.0;
-        if (j >= i)
-            for (int k = i; k <= j; k++) s = fma(M[i * n + k], R1[k * n + j], s);
-        R[e] = s;
-    }
-    if (tid < 32) {
-        // forward substitution with R2^T, one warp
-        for (int i = 0; i < n; i++) {
+    // pass 2: R = R2 R1 (upper x upper) by all warps but the last, which does
+    // Q^T f = R2^-T z (forward substitution with R2^T) at the same time
+    for (int i = tid; i < n; i += nt) wrk[i] = 1.0 / M[i * n + i];
+    __syncthreads();
+    const int nprod = nt - 32;
+    if (tid < nprod) {
+        for (int e = tid; e < n2; e += nprod) {
+            const int i = e / n, j = e % n;
             double s = 0.0;
-            for (int k = tid; k < i; k += 32) s = fma(M[k * n + i], qtf[k], s);
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-            if (tid == 0) qtf[i] = (qtf[i] - s) / M[i * n + i];
-            __syncwarp();
+            if (j >= i)
+                for (int k = i; k <= j; k++) s = fma(M[i * n + k], R1[k * n + j], s);
+            R[e] = s;
         }
+    } else {
+        // lane l owns entries k = l, l + 32, ... of the solution (registers)
+        const int lane = tid & 31;
+        double qc[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) qc[q] = (lane + 32 * q < n) ? qtf[lane + 32 * q] : 0.0;
+        // right-looking: once entry i is final it is taken out of the later
+        // ones along ROW i of R2 (contiguous in memory, no reduction)
+        for (int i = 0; i < n; i++) {
+            double v = 0.0;
+#pragma unroll
+            for (int q = 0; q < 8; q++)
+                if ((i >> 5) == q) v = qc[q] * wrk[i];
+            v = __shfl_sync(0xffffffffu, v, i & 31);
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                const int k = lane + 32 * q;
+                if (k == i) qc[q] = v;
+                else if (k > i && k < n) qc[q] = fma(-M[i * n + k], v, qc[q]);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 8; q++)
+            if (lane + 32 * q < n) qtf[lane + 32 * q] = qc[q];
     }
     if (tid == 0) info[0] = 0.0;
 }

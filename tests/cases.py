@@ -1055,9 +1055,12 @@ def check_tall_edge_cases_vs_oracle(lib, dev):
     iterations along an ill-conditioned valley: 1-ulp noise on f changes its
     nfev 318 -> 324 / 969 at kappa = 1e6 and x by 16 %), so for dogbox the
     gates are: no failure, feasible, and a cost no worse than the reference's
-    by more than its own self-sensitivity (1e-2); at kappa = 1e6 the reference
-    ends with status 2 after 976 evaluations, and with status 0 (budget of
-    2400 exhausted, at a LOWER cost) in 4 of 6 runs with 1-ulp noise on f."""
+    by more than its own self-sensitivity; at kappa = 1e6 the reference
+    ends with status 2 after 976 evaluations, with status 0 (budget of
+    2400 exhausted, at a 6 - 7 % LOWER cost) in 13 of 16 runs with 1-ulp noise
+    on f, and with status 2 after 195 - 306 evaluations at an 8 - 12 % HIGHER
+    cost in 11 of 40 runs with 1-ulp noise on f and J
+    (tests/golden/kappa_dogbox_sensitivity.json)."""
     from oracle import blsq_oracle as orc
     rng = np.random.default_rng(12)
     out = {}
@@ -1120,6 +1123,8 @@ def check_tall_edge_cases_vs_oracle(lib, dev):
         assert np.allclose(res.x.cpu().numpy(), r.x, rtol=1e-8, atol=0)
         assert abs(res.obj_value - r.obj_value) <= 1e-8 * r.obj_value
     # ---- kappa sweep ----
+    with open(os.path.join(GOLDEN, "kappa_dogbox_sensitivity.json")) as fh:
+        sens = json.load(fh)
     m, n = 3000, 24
     for kappa in (1e6, 1e8, 1e10, 1e12):
         U, _ = np.linalg.qr(rng.standard_normal((m, n)))
@@ -1150,7 +1155,13 @@ def check_tall_edge_cases_vs_oracle(lib, dev):
                 assert s["x_rel"] < max(1e-8, 10 * kappa * 2.2e-16), (kappa, s)
             else:
                 assert res.status >= 0, (kappa, s)
-                assert res.obj_value <= r.obj_value * 1.01, (kappa, s)
+                # kappa = 1e6: the worst of 56 runs of the reference algorithm
+                # itself under 1-ulp noise (tests/golden/kappa_dogbox_sensitivity.py:
+                # cost 0.93 ... 1.116 of the unperturbed run, 195 ... 2400
+                # evaluations) with a 10 % margin; elsewhere 1 %
+                gate = 1.1 * sens["cost_ratio_max"] if kappa == 1e6 else 1.01
+                assert sens["unperturbed"]["nfev"] == 976 or kappa != 1e6
+                assert res.obj_value <= r.obj_value * gate, (kappa, s)
     return out
 
 
