@@ -312,6 +312,17 @@ class ClockSampler:
             self._stop.wait(0.02 if self._nvml is not None else 0.2)
 
     def __enter__(self):
+        # the first NVML queries of a process are the slow ones (they take the
+        # driver's lock for 10-100 ms and stall a concurrent launch path): make
+        # them here, before anything is timed
+        if self._nvml is not None:
+            for _ in range(8):
+                try:
+                    self._sample_nvml()
+                except Exception:
+                    break
+                time.sleep(0.005)
+            self.rows.clear()
         self._t = threading.Thread(target=self._run, daemon=True)
         self._t.start()
         return self
