@@ -812,8 +812,13 @@ def run_batched(args, w, wname, steps, warmup, B, cpu_baseline=True, inlined=Fal
         return float(t.item())
 
     # ---- device-resident timing -----------------------------------------
-    for _ in range(warmup):
-        solve(y_dev, x0_dev)
+    # the warm-up keeps the previous result alive while the next solve runs,
+    # exactly as the timed loop does: with results dropped at once the second
+    # TIMED step was the first to need a second set of result buffers and paid
+    # the allocator's cudaMalloc for it (sporadic 20 - 150 ms on that step)
+    outs = None
+    for _ in range(max(warmup, 2)):
+        outs = solve(y_dev, x0_dev)
     barrier()
     launches = 0
     rounds = 0
@@ -822,7 +827,7 @@ def run_batched(args, w, wname, steps, warmup, B, cpu_baseline=True, inlined=Fal
         # first NVML queries cost the launch path 10-100 ms once (seen as a
         # slow second step in 4 of 6 runs when the thread started with the
         # timed region)
-        solve(y_dev, x0_dev)
+        outs = solve(y_dev, x0_dev)
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = torch.cuda.Event(enable_timing=True)
         barrier()
