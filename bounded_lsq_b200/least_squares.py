@@ -137,6 +137,10 @@ def least_squares_batched(fun, x0, jac='2-point', bounds=(-float('inf'), float('
     are called on the A <= B problems still running (rows in problem order);
     wrap per-problem tensors in ``PerProblem`` so they are gathered alike.
     Every field of the result has a leading B dimension.
+
+    ``options``: ``chunk`` (solve the batch that many problems at a time),
+    ``x_covariance``, ``h2d_chunks`` / ``device`` (host inputs), and the driver
+    knobs of ``batched.solve_batched``.
     """
     lib = _lib if _lib is not None else L.get_lib()
     _validate_common(method, bounds, jac)
@@ -150,10 +154,66 @@ def least_squares_batched(fun, x0, jac='2-point', bounds=(-float('inf'), float('
         target = None
     guard = torch.cuda.device(target) if target is not None else \
         lib.device_guard(None)
+    chunk = options.pop("chunk", None)
     with guard:
+        if chunk is not None and isinstance(x0, torch.Tensor) and x0.dim() == 2 \
+                and x0.shape[0] > int(chunk) > 0:
+            return _least_squares_chunked(lib, int(chunk), fun, x0, jac, bounds, method,
+                                          ftol, xtol, gtol, max_nfev, scaling, diff_step,
+                                          args, kwargs, options)
         return _least_squares_batched(lib, fun, x0, jac, bounds, method, ftol, xtol,
                                       gtol, max_nfev, scaling, diff_step, args,
                                       kwargs, options)
+
+
+def _least_squares_chunked(lib, chunk, fun, x0, jac, bounds, method, ftol, xtol, gtol,
+                           max_nfev, scaling, diff_step, args, kwargs, options):
+    """``options={'chunk': K}``: the batch is solved K problems at a time and the
+    results are concatenated -- the working set of a round (callback outputs,
+    records) is that of K problems whatever B is (config C3: 10M problems in 1M
+    chunks).  Host inputs are staged once for the whole batch; a chunk starts
+    when its own copies have landed."""
+    B = x0.shape[0]
+    plan = None
+    if lib.requires_cuda and not x0.is_cuda:
+        x0, args, kwargs, plan = _stage_host_inputs(x0, args, kwargs, options)
+    else:
+        options.pop("h2d_chunks", None)
+        options.pop("device", None)
+
+    def part(v, c0, c1):
+        if isinstance(v, PerProblem):
+            return PerProblem(v.tensor[c0:c1])
+        return v
+
+    def bound(b, c0, c1):
+        shape = getattr(b, "shape", ())
+        if len(shape) == 2 and shape[0] == B:
+            return b[c0:c1]
+        return b
+    outs = []
+    for c0 in range(0, B, chunk):
+        c1 = min(B, c0 + chunk)
+        if plan is not None:
+            cur = torch.cuda.current_stream(x0.device)
+            if plan.x0_event is not None:
+                cur.wait_event(plan.x0_event)
+            for p0, p1, ev in plan:
+                if ev is not None and p0 < c1 and p1 > c0:
+                    cur.wait_event(ev)
+        outs.append(_least_squares_batched(
+            lib, fun, x0[c0:c1], jac, (bound(bounds[0], c0, c1), bound(bounds[1], c0, c1)),
+            method, ftol, xtol, gtol, max_nfev, scaling, diff_step,
+            tuple(part(v, c0, c1) for v in args),
+            {k: part(v, c0, c1) for k, v in dict(kwargs).items()}, dict(options)))
+    res = OptimizeResult(outs[0])
+    for key, v in outs[0].items():
+        if isinstance(v, torch.Tensor) and v.dim() >= 1 and v.shape[0] == outs[0].x.shape[0]:
+            res[key] = torch.cat([o[key] for o in outs])
+    for key in ("rounds", "kernel_launches"):
+        if key in res:
+            res[key] = sum(o[key] for o in outs)
+    return res
 
 
 def _least_squares_batched(lib, fun, x0, jac, bounds, method, ftol, xtol, gtol,

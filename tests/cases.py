@@ -1277,3 +1277,35 @@ def check_mode_routing(lib, dev):
     with pytest.raises(ValueError):
         least_squares(fun_t, T(x0, dev), options=dict(mode="wide"), _lib=lib)
     return out
+
+
+def check_chunked_batch(lib, dev):
+    """options={'chunk': K}: the batch solved K problems at a time gives the bits
+    of the one-piece solve (per-problem arithmetic does not depend on the
+    batch), with shared and with per-problem bounds, for device and (on the
+    GPU) pinned host inputs."""
+    model = ExpDecay2()
+    B = 2500
+    _, y = model.make_data(B, seed=33)
+    X0 = np.tile(model.x0, (B, 1))
+    lbB = np.tile(model.lb, (B, 1))
+    ubB = np.tile(model.ub, (B, 1))
+    ubB[::3, 2] = 1.2                                 # a per-problem bound that binds
+    for method, jac in (("trf", model.jac_t), ("dogbox", "2-point")):
+        for bounds in ((model.lb, model.ub), (T(lbB, dev), T(ubB, dev))):
+            kw = dict(jac=jac, bounds=bounds, method=method, _lib=lib)
+            one = least_squares_batched(model.fun_t, T(X0, dev), args=(PerProblem(T(y, dev)),), **kw)
+            variants = [least_squares_batched(model.fun_t, T(X0, dev),
+                                              args=(PerProblem(T(y, dev)),),
+                                              options=dict(chunk=700), **kw)]
+            if dev.type == "cuda":
+                variants.append(least_squares_batched(
+                    model.fun_t, torch.from_numpy(X0).pin_memory(),
+                    args=(PerProblem(torch.from_numpy(y).pin_memory()),),
+                    options=dict(chunk=1000, h2d_chunks=2, device=dev), **kw))
+            for r in variants:
+                assert r.x.shape == (B, model.n) and r.fun.shape == one.fun.shape
+                for fld in ("x", "obj_value", "optimality", "status", "nfev", "njev",
+                            "active_mask", "fun", "success"):
+                    assert bits(r[fld].cpu().numpy(), one[fld].cpu().numpy()), (method, fld)
+                assert r.rounds >= one.rounds

@@ -108,6 +108,10 @@ def test_mode_routing(lib):
     cases.check_mode_routing(lib, DEV)
 
 
+def test_chunked_batch(lib):
+    cases.check_chunked_batch(lib, DEV)
+
+
 def test_compact_batched(lib):
     cases.check_compact_batched(lib, DEV)
 

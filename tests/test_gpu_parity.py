@@ -283,6 +283,10 @@ def test_mode_routing(lib, dev):
     cases.check_mode_routing(lib, dev)
 
 
+def test_chunked_batch(lib, dev):
+    cases.check_chunked_batch(lib, dev)
+
+
 def test_compact_batched(lib, dev):
     cases.check_compact_batched(lib, dev)
 
