@@ -248,6 +248,35 @@ def run_reference_arm(args, w):
     print(json.dumps(line))
 
 
+# ------------------------------------------------------------ affinity ----
+
+def pin_rank_to_gpu_cpus(local):
+    """N > 1: the driver thread of this rank runs on the host cores NVML names
+    as local to its GPU (torchrun does not bind ranks).  BLSQ_BENCH_PIN=0
+    turns it off.  Returns what was done, for the JSON line."""
+    if os.environ.get("BLSQ_BENCH_PIN", "1") == "0":
+        return "off"
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        uuid = str(torch.cuda.get_device_properties(local).uuid)
+        if not uuid.startswith("GPU-"):
+            uuid = "GPU-" + uuid
+        h = pynvml.nvmlDeviceGetHandleByUUID(uuid)
+        ncpu = os.cpu_count() or 1
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        near = [i for i in range(ncpu) if (mask[i // 64] >> (i % 64)) & 1]
+        allowed = sorted(os.sched_getaffinity(0))
+        cpus = [c for c in near if c in allowed]
+        if not cpus or len(cpus) == len(allowed):
+            return "all %d allowed cores are local to the GPU" % len(allowed)
+        os.sched_setaffinity(0, cpus)
+        return "cores %d-%d of %d" % (cpus[0], cpus[-1], len(allowed))
+    except Exception as e:                      # reporting only
+        return "unavailable (%r)" % (e,)
+
+
 # ------------------------------------------------------------ clocks ------
 
 class ClockSampler:
@@ -679,11 +708,15 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    pinned = None
     if world > 1:
+        pinned = pin_rank_to_gpu_cpus(local)
         dist.init_process_group("nccl", device_id=dev)
 
     line = run_batched(args, w, args.workload, args.steps, args.warmup,
                        args.batch or w["B"], cpu_baseline=not args.no_cpu_baseline)
+    if line is not None and pinned is not None:
+        line["config"]["driver_thread_affinity"] = pinned
 
     # the other half of BASELINE.json's metric (TRF iterations/s at m=16M,
     # n=64) rides along on the default run as the "tall" object, and a short
@@ -749,10 +782,15 @@ def run_batched(args, w, wname, steps, warmup, B, cpu_baseline=True, inlined=Fal
     n, m = w["n"], w["m"]
     method = w["method"]
 
-    # synthetic data of the named shape, generated on the host once
-    # (seeded per rank: different problems on every GPU)
+    # synthetic data of the named shape, generated on the host once.  Every
+    # GPU solves the SAME pool (weak scaling: per-GPU work exactly fixed).  With
+    # a seed per rank the pools differ in their slowest problem -- C2: 113
+    # evaluations for seed 10000, 254 for 10001 (oracle) -- and a solve runs as
+    # many latency-sized tail rounds as its slowest problem needs: rank 1's
+    # steps took 22.3 ms against rank 0's 19.0 for that reason alone.
+    # BLSQ_BENCH_SEED_PER_RANK=1 restores the per-rank pools.
     t_gen = time.perf_counter()
-    rng_seed = 10_000 + rank
+    rng_seed = 10_000 + (rank if os.environ.get("BLSQ_BENCH_SEED_PER_RANK") == "1" else 0)
     ngen = min(B, 262_144)              # tile a 256k-problem pool up to B
     _, ypool = model.make_data(ngen, seed=rng_seed)
     reps = (B + ngen - 1) // ngen
@@ -844,6 +882,16 @@ def run_batched(args, w, wname, steps, warmup, B, cpu_baseline=True, inlined=Fal
         barrier()
     dev_ms = reduce_max(e0.elapsed_time(e1))
     per_step_ms = [a.elapsed_time(b) for a, b in zip(marks, marks[1:])]
+    by_rank = None
+    if world > 1:
+        # every rank's own steps: the line's time is the MAX over ranks of the
+        # whole region, so one slow rank (or one stalled step on any of them)
+        # sets it
+        mine = torch.tensor(per_step_ms, dtype=torch.float64, device=dev)
+        allr = torch.empty((world, steps), dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(allr.view(-1), mine)
+        by_rank = {"mean": [round(float(v), 3) for v in allr.mean(1)],
+                   "max": [round(float(v), 3) for v in allr.max(1).values]}
     value = world * B * steps / (dev_ms * 1e-3)
     status = torch.cat([o.status for o in outs])
     nfev_mean = float(torch.cat([o.nfev for o in outs]).double().mean())
@@ -1020,11 +1068,12 @@ def run_batched(args, w, wname, steps, warmup, B, cpu_baseline=True, inlined=Fal
             static_config(w, B, chunk, "inlined" if inlined else args.callbacks),
             l2="inputs (J+f per round: %.1f GB) exceed the 126 MB L2"
                % (chunk * m * (n + 1) * 8 / 1e9),
-            data_pool="%d distinct seeded problems per GPU tiled to %d "
-                      "(same traffic; host generation time)" % (ngen, B),
+            data_pool="%d distinct seeded problems tiled to %d (same traffic; host "
+                      "generation time); the same pool on every GPU" % (ngen, B),
             mean_nfev=nfev_mean, mean_njev=njev_mean, converged_frac=converged,
             rounds_per_step=rounds / steps,
-            per_step_ms=[round(v, 3) for v in per_step_ms]),
+            per_step_ms=[round(v, 3) for v in per_step_ms],
+            **({"per_step_ms_by_rank": by_rank} if by_rank else {})),
         "e2e": {"value": e2e_value, "unit": "fits/s",
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms / steps, "per_step_ms": e2e_steps,
