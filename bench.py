@@ -290,7 +290,8 @@ class ClockSampler:
          "clocks_event_reasons.sw_power_cap")
     # nvmlClocksEventReason bits
     BITS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40),
-            ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
+            ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4),
+            ("hw_power_brake_slowdown", 0x80))
 
     def __init__(self, index):
         self.index = index
@@ -365,10 +366,12 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
         sm = sorted(float(r[0]) for r in self.rows if r[0].replace('.', '').isdigit())
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
-                 "sw_power_cap"]
+                 "sw_power_cap", "hw_power_brake_slowdown"]
         reasons = [n for i, n in enumerate(names)
-                   if any(r[2 + i].lower().startswith("active") for r in self.rows)]
+                   if any(len(r) > 2 + i and r[2 + i].lower().startswith("active")
+                          for r in self.rows)]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None,
+                "sm_min_mhz": sm[0] if sm else None,
                 "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
                 "samples": len(self.rows),
                 "source": "nvml" if self._nvml is not None else "nvidia-smi"}
