@@ -293,37 +293,47 @@ class ClockSampler:
             ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4),
             ("hw_power_brake_slowdown", 0x80))
 
-    def __init__(self, index):
+    def __init__(self, index, world=1, rank=0):
+        """N > 1: ONE sampler for the job -- rank 0's thread reads the clocks of
+        all `world` GPUs of the box; the other ranks make no NVML call at all
+        (eight processes polling NVML were the one thing the 8-GPU bench did
+        that tools/diag_first_step.py, which has no slow first step, did not)."""
         self.index = index
         self.rows = []
         self._stop = threading.Event()
         self._t = None
         self._nvml = None
-        self._h = None
+        self._hs = []
+        self.active = rank == 0
+        self.gpus = list(range(world)) if world > 1 else [index]
+        if not self.active:
+            return
         try:
             import pynvml
             import torch
             pynvml.nvmlInit()
-            uuid = str(torch.cuda.get_device_properties(index).uuid)
-            if not uuid.startswith("GPU-"):
-                uuid = "GPU-" + uuid
-            self._h = pynvml.nvmlDeviceGetHandleByUUID(uuid)
+            for i in self.gpus:
+                uuid = str(torch.cuda.get_device_properties(i).uuid)
+                if not uuid.startswith("GPU-"):
+                    uuid = "GPU-" + uuid
+                self._hs.append(pynvml.nvmlDeviceGetHandleByUUID(uuid))
             self._max = float(pynvml.nvmlDeviceGetMaxClockInfo(
-                self._h, pynvml.NVML_CLOCK_SM))
+                self._hs[0], pynvml.NVML_CLOCK_SM))
             self._nvml = pynvml
         except Exception:
             self._nvml = None
 
     def _sample_nvml(self):
         nv = self._nvml
-        sm = nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)
-        try:
-            mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h)
-        except Exception:
-            mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
-        row = [str(float(sm)), str(self._max)]
-        row += ["Active" if mask & bit else "Not Active" for _, bit in self.BITS]
-        self.rows.append(row)
+        for h in self._hs:
+            sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+            try:
+                mask = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+            except Exception:
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+            row = [str(float(sm)), str(self._max)]
+            row += ["Active" if mask & bit else "Not Active" for _, bit in self.BITS]
+            self.rows.append(row)
 
     def _run(self):
         while not self._stop.is_set():
@@ -342,6 +352,8 @@ class ClockSampler:
             self._stop.wait(0.02 if self._nvml is not None else 0.2)
 
     def __enter__(self):
+        if not self.active:
+            return self
         # the first NVML queries of a process are the slow ones (they take the
         # driver's lock for 10-100 ms and stall a concurrent launch path): make
         # them here, before anything is timed
@@ -359,7 +371,8 @@ class ClockSampler:
 
     def __exit__(self, *a):
         self._stop.set()
-        self._t.join(timeout=6)
+        if self._t is not None:
+            self._t.join(timeout=6)
 
     def summary(self):
         if not self.rows:
@@ -373,7 +386,7 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None,
                 "sm_min_mhz": sm[0] if sm else None,
                 "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
-                "samples": len(self.rows),
+                "samples": len(self.rows), "gpus_sampled": len(self.gpus),
                 "source": "nvml" if self._nvml is not None else "nvidia-smi"}
 
 
@@ -527,7 +540,7 @@ def run_tall(args, w, standalone=True, light=False):
     its = 0
     launches = 0
     nfev = 0
-    with ClockSampler(local) as clk:
+    with ClockSampler(local, world, rank) as clk:
         solve()                            # untimed, sampler thread running (see run_batched)
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = torch.cuda.Event(enable_timing=True)
@@ -863,7 +876,7 @@ def run_batched(args, w, wname, steps, warmup, B, cpu_baseline=True, inlined=Fal
     barrier()
     launches = 0
     rounds = 0
-    with ClockSampler(local) as clk:
+    with ClockSampler(local, world, rank) as clk:
         # one more untimed solve with the sampler thread already running: its
         # first NVML queries cost the launch path 10-100 ms once (seen as a
         # slow second step in 4 of 6 runs when the thread started with the
